@@ -1,0 +1,151 @@
+/* stb200.h — C ABI of the B200-native window-attention hot path (libstb200.so).
+ *
+ * Drop-in boundary for the `extern "C"` launchers of the reference's pointops2 extension
+ * (paths under /root/reference/lib/pointops2/src).  Every entry point cites the reference
+ * declaration it replaces.  Conventions shared by all entry points:
+ *
+ *   - plain C: device pointers + sizes, no torch types.  float = fp32, int = int32, contiguous.
+ *   - trailing `void *stream` is a cudaStream_t (NULL = legacy default stream, what the
+ *     reference always used: `<<<blocks, threads, 0>>>`).  Calls are asynchronous.
+ *   - return value: 0 on success, an STB200_ERR_* code otherwise (the reference returned void and
+ *     threw a `const char*` for unsupported head dims); stb200_last_error() gives the message.
+ *   - outputs are caller-allocated like in the reference (functions/pointops.py:157,188-189,...).
+ *     Outputs that the reference overwrites are overwritten; outputs it accumulates into
+ *     (grad_k, grad_v, grad_table*) are ACCUMULATED INTO here too, so callers keep zero-filling
+ *     them exactly as functions/pointops.py does.
+ *   - `n_max` is accepted for signature compatibility and ignored (no launch shape depends on it,
+ *     so segments longer than 1024 pairs are fine).
+ *   - head dim (C/h or hdim) must be 16 or 32, as in the reference (attention_cuda_kernel_v2.cu:108-117).
+ *   - rel_idx values must lie in [0, L); out-of-range values are clamped for memory safety
+ *     (the reference reads out of bounds; its Python asserts the range, stratified_transformer.py:189-190).
+ *
+ * Additions relative to the reference ABI (needed by a scatter-free design, documented in DESIGN.md):
+ *   - `L` (table length) on every entry point that takes a table: tables are staged in shared memory.
+ *   - the "transposed CSR" (pairs grouped by key) on backward entry points: grad_k / grad_v are
+ *     computed by gathering over a key's incoming pairs instead of float atomics.  Build it once per
+ *     index set with stb200_transpose_csr().
+ */
+#ifndef STB200_H
+#define STB200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STB200_OK 0
+#define STB200_ERR_HEAD_DIM 1   /* head dim not in {16, 32} */
+#define STB200_ERR_ARG 2        /* null pointer / negative size / inconsistent sizes */
+#define STB200_ERR_CUDA 3       /* a CUDA runtime call failed; see stb200_last_error() */
+#define STB200_ERR_WORKSPACE 4  /* workspace too small; query the size with the *_workspace_bytes call */
+
+const char *stb200_last_error(void);
+/* number of kernels this library launched since load (bench.py's "gpu_launches") */
+long long stb200_launch_count(void);
+int stb200_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Transposed CSR: pairs grouped by key.  For key j, t in [t_offsets[j], t_offsets[j+1]) enumerates its
+ * incoming pairs in ascending pair id: t_pair[t] = m, t_index0[t] = query id of pair m.
+ * (No reference counterpart: the reference scatters with atomicAdd, e.g. attention_cuda_kernel_v2.cu:84.)
+ * workspace: stb200_transpose_csr_workspace_bytes(N, M) bytes of device scratch. */
+size_t stb200_transpose_csr_workspace_bytes(int N, int M);
+int stb200_transpose_csr(int N, int M, const int *index0_offsets, const int *index1,
+                         int *t_offsets /*[N+1]*/, int *t_pair /*[M]*/, int *t_index0 /*[M]*/,
+                         void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * attention_step1 v2 — replaces attention_step1_forward_cuda_launcher_v2 /
+ * attention_step1_backward_cuda_launcher_v2 (attention_v2/attention_cuda_kernel_v2.h:18-19).
+ * attn[m,h] = <q[i0(m),h,:], k[index1[m],h,:]>,  m in [index0_offsets[n], index0_offsets[n+1]). */
+int stb200_attention_step1_forward_v2(int N, int M, int h, int C, unsigned int n_max,
+                                      const float *q, const float *k, const int *index0_offsets,
+                                      const int *index1, float *attn, void *stream);
+int stb200_attention_step1_backward_v2(int N, int M, int h, int C, unsigned int n_max,
+                                       const float *grad_out, const int *index0_offsets, const int *index1,
+                                       const float *q, const float *k, float *grad_q, float *grad_k,
+                                       const int *t_offsets, const int *t_pair, const int *t_index0,
+                                       void *stream);
+
+/* dot_prod_with_idx v3 — replaces dot_prod_with_idx_forward_cuda_launcher_v3 / ..._backward_..._v3
+ * (rpe_v2/relative_pos_encoding_cuda_kernel_v2.h:23-24).
+ * out[m,h] = <q[i0],Eq(m,h)> + <k[i1],Ek(m,h)>, E_t = T_t[r0,h,:,0] + T_t[r1,h,:,1] + T_t[r2,h,:,2]. */
+int stb200_dot_prod_with_idx_forward_v3(int N, int M, int h, int hdim, int n_max, int L,
+                                        const float *q, const int *index_q_offsets, const float *k,
+                                        const int *index_k, const float *table_q, const float *table_k,
+                                        const int *rel_idx, float *output, void *stream);
+int stb200_dot_prod_with_idx_backward_v3(int N, int M, int h, int hdim, int n_max, int L,
+                                         const float *grad_out, const float *q, const int *index_q_offsets,
+                                         const float *k, const int *index_k, const float *table_q,
+                                         const float *table_k, const int *rel_idx, float *grad_q,
+                                         float *grad_k, float *grad_table_q, float *grad_table_k,
+                                         const int *t_offsets, const int *t_pair, const int *t_index0,
+                                         void *stream);
+
+/* attention_step2_with_rel_pos_value v2 — replaces attention_step2_with_rel_pos_value_forward_cuda_launcher_v2
+ * / ..._backward_..._v2 (rpe_v2/relative_pos_encoding_cuda_kernel_v2.h:26-27).
+ * out[n,h,:] = sum_seg attn[m,h] * (v[index1[m],h,:] + Ev(m,h,:)). */
+int stb200_attention_step2_with_rel_pos_value_forward_v2(int N, int M, int h, int hdim, int n_max, int L,
+                                                         const float *attn, const float *v,
+                                                         const int *index0_offsets, const int *index1,
+                                                         const float *table, const int *rel_idx,
+                                                         float *output, void *stream);
+int stb200_attention_step2_with_rel_pos_value_backward_v2(int N, int M, int h, int hdim, int n_max, int L,
+                                                          const float *grad_out, const int *index0_offsets,
+                                                          const int *index1, const float *attn, const float *v,
+                                                          const float *table, const int *rel_idx,
+                                                          float *grad_attn, float *grad_v, float *grad_table,
+                                                          const int *t_offsets, const int *t_pair,
+                                                          const int *t_index0, void *stream);
+
+/* Segment softmax over the pairs of each query, per head — replaces the third-party
+ * torch_scatter.scatter_softmax(src=attn_flat, index=index_0, dim=0) call and the preceding
+ * `attn_flat + relative_position_bias` (model/stratified_transformer.py:203,205).
+ * p = softmax_seg(a + b); b may be NULL.  Backward: gs = p * (gp - sum_seg p*gp). */
+int stb200_segment_softmax_forward(int N, int M, int h, const float *a, const float *b,
+                                   const int *index0_offsets, float *p, void *stream);
+int stb200_segment_softmax_backward(int N, int M, int h, const float *p, const float *grad_p,
+                                    const int *index0_offsets, float *grad_s, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * v1 entry points (explicit, possibly unsorted index0/index1; API completeness).
+ * Replace attention/attention_cuda_kernel.h:17-21 and rpe/relative_pos_encoding_cuda_kernel.h launchers. */
+int stb200_attention_step1_forward(int N, int M, int h, int C, const float *q, const float *k,
+                                   const int *index0, const int *index1, float *attn, void *stream);
+int stb200_attention_step1_backward(int N, int M, int h, int C, const float *grad_out, const int *index0,
+                                    const int *index1, const float *q, const float *k, float *grad_q,
+                                    float *grad_k, void *stream);
+int stb200_attention_step2_forward(int N, int M, int h, int C, const float *attn, const float *v,
+                                   const int *index0, const int *index1, float *output, void *stream);
+int stb200_attention_step2_backward(int N, int M, int h, int C, const float *grad_out, const int *index0,
+                                    const int *index1, const float *attn, const float *v, float *grad_attn,
+                                    float *grad_v, void *stream);
+int stb200_dot_prod_with_idx_forward(int N, int M, int h, int hdim, int L, const float *q, const int *index,
+                                     const float *table, const int *rel_idx, float *output, void *stream);
+int stb200_dot_prod_with_idx_backward(int N, int M, int h, int hdim, int L, const float *grad_out,
+                                      const float *q, const int *index, const float *table,
+                                      const int *rel_idx, float *grad_q, float *grad_table, void *stream);
+int stb200_attention_step2_with_rel_pos_value_forward(int N, int M, int h, int hdim, int L, const float *attn,
+                                                      const float *v, const int *index0, const int *index1,
+                                                      const float *table, const int *rel_idx, float *output,
+                                                      void *stream);
+int stb200_attention_step2_with_rel_pos_value_backward(int N, int M, int h, int hdim, int L,
+                                                       const float *grad_out, const int *index0,
+                                                       const int *index1, const float *attn, const float *v,
+                                                       const float *table, const int *rel_idx,
+                                                       float *grad_attn, float *grad_v, float *grad_table,
+                                                       void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Furthest point sampling — replaces furthestsampling_cuda_launcher (sampling/sampling_cuda_kernel.h:10).
+ * Bit-exact with the reference kernel including its tie behaviour.  `n` = largest scene size (selects the
+ * reference's virtual block size that defines tie order); `tmp` [N] f32 scratch is accepted and left
+ * untouched (the running minimum distances live on chip); idx [new_offset[b-1]] int32 out. */
+int stb200_furthestsampling(int b, int n, const float *xyz, const int *offset, const int *new_offset,
+                            float *tmp, int *idx, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STB200_H */

@@ -1,0 +1,86 @@
+"""ctypes binding of libstb200.so (the C ABI declared in include/stb200.h).
+
+There is deliberately NO fallback: if the shared library is missing or a call fails, this raises.
+Nothing here imports `oracle/`.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libstb200.so")
+
+_c_int, _c_uint, _c_void_p, _c_size_t = ctypes.c_int, ctypes.c_uint, ctypes.c_void_p, ctypes.c_size_t
+P = _c_void_p
+
+# name -> argtypes (every function returns int unless listed in _RESTYPES)
+_SIGNATURES = {
+    "stb200_transpose_csr": [_c_int, _c_int, P, P, P, P, P, P, _c_size_t, P],
+    "stb200_attention_step1_forward_v2": [_c_int] * 4 + [_c_uint] + [P] * 6,
+    "stb200_attention_step1_backward_v2": [_c_int] * 4 + [_c_uint] + [P] * 11,
+    "stb200_dot_prod_with_idx_forward_v3": [_c_int] * 6 + [P] * 9,
+    "stb200_dot_prod_with_idx_backward_v3": [_c_int] * 6 + [P] * 16,
+    "stb200_attention_step2_with_rel_pos_value_forward_v2": [_c_int] * 6 + [P] * 8,
+    "stb200_attention_step2_with_rel_pos_value_backward_v2": [_c_int] * 6 + [P] * 14,
+    "stb200_segment_softmax_forward": [_c_int] * 3 + [P] * 5,
+    "stb200_segment_softmax_backward": [_c_int] * 3 + [P] * 5,
+    "stb200_attention_step1_forward": [_c_int] * 4 + [P] * 6,
+    "stb200_attention_step1_backward": [_c_int] * 4 + [P] * 8,
+    "stb200_attention_step2_forward": [_c_int] * 4 + [P] * 6,
+    "stb200_attention_step2_backward": [_c_int] * 4 + [P] * 8,
+    "stb200_dot_prod_with_idx_forward": [_c_int] * 5 + [P] * 6,
+    "stb200_dot_prod_with_idx_backward": [_c_int] * 5 + [P] * 8,
+    "stb200_attention_step2_with_rel_pos_value_forward": [_c_int] * 5 + [P] * 8,
+    "stb200_attention_step2_with_rel_pos_value_backward": [_c_int] * 5 + [P] * 11,
+    "stb200_furthestsampling": [_c_int, _c_int] + [P] * 6,
+}
+_RESTYPES = {
+    "stb200_last_error": (ctypes.c_char_p, []),
+    "stb200_launch_count": (ctypes.c_longlong, []),
+    "stb200_version": (_c_int, []),
+    "stb200_transpose_csr_workspace_bytes": (_c_size_t, [_c_int, _c_int]),
+}
+
+EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + list(_RESTYPES))
+
+_lib = None
+
+
+class Stb200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load libstb200.so; raise loudly when it has not been built (python __graft_entry__.py build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Stb200Error(
+            f"{LIB_PATH} not found: the CUDA extension is not built. Run `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (or `make -C stratified_transformer_b200/csrc`). There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = _c_int
+    for name, (restype, argtypes) in _RESTYPES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = restype
+    _lib = lib
+    return lib
+
+
+def call(name: str, *args):
+    """Call an int-returning entry point and turn a non-zero status into an exception."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.stb200_last_error().decode(errors="replace")
+        raise Stb200Error(f"{name} failed (code {rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(load().stb200_launch_count())

@@ -1,0 +1,618 @@
+// Variable-length window attention over a CSR pair list: the v2/v3 pointops2 operators, fwd + bwd.
+//
+// What is computed is specified by the reference kernels (paths under /root/reference/lib/pointops2/src):
+//   attention_v2/attention_cuda_kernel_v2.cu:7-91        step1 fwd/bwd
+//   rpe_v2/relative_pos_encoding_cuda_kernel_v2.cu:247-340   dot_prod_with_idx v3 fwd/bwd
+//   rpe_v2/relative_pos_encoding_cuda_kernel_v2.cu:397-484   step2 with rel-pos value v2 fwd/bwd
+// How it is computed is new.  The reference launches one CTA per (query, head) with one thread per
+// pair, re-reads index1 inside the channel loop, sums through shared/global float atomics and hits
+// the rel-pos tables with 96 scalar global loads per pair-head.  Here:
+//   * three generic warp-per-segment kernels cover all ten operators:
+//       seg_dot     per pair-head scalar   = <x_row, y_row + Ex> + <y_row, Ey>
+//       seg_reduce  per row vector         = sum over the row's pairs  w * (y_row + E)
+//       table_grad  per table              = sum_n  X[n] (x) hist_n   (a small dense GEMM, see below)
+//   * a head row (16/32 floats) is split over 4/8 lanes as float4, so a warp works on 8/4 pairs at a time
+//     and every gathered 64/128 B row chunk is one fully used set of sectors;
+//   * rel-pos tables are staged once per CTA in shared memory, re-laid out [axis][l][head][c] so the three
+//     lookups per channel quad are three LDS.128 instead of twelve stride-3 scalar loads;
+//   * grad_k / grad_v gather over the transposed CSR (pairs grouped by key) instead of scattering with
+//     atomics, grad_q / grad_attn are segment-local register reductions;
+//   * table gradients use  gT[l,h,c,a] = sum_n X[n,h,c] * W_a[n,l,h],  W_a[n,l,h] = sum_{m in seg(n), r[m,a]=l} w[m,h]:
+//     a per-row histogram (3 scalar adds per pair-head instead of 3*d atomics) followed by a register-tiled
+//     fp32 outer-product accumulation; one flush of red.global.add per CTA at the end.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace stb200 {
+
+constexpr int kThreads = 256;
+constexpr int kRowsPerChunk = 64;  // rows (queries or keys) a CTA takes per grid-stride step
+
+struct SegParams {
+    int N, h, L;
+    const float *X;        // rows indexed by the segment owner n            [N, h, D]
+    const float *Y;        // rows indexed by gather_idx                      [*, h, D]
+    const float *w;        // per pair-head weights                           [M, h]
+    const int *offsets;    // CSR offsets of the segment owner                [N+1]
+    const int *gather_idx; // row id in Y per segment slot                    [M]
+    const int *pair_id;    // pair id per segment slot (transposed CSR) or null
+    const float *Tx, *Ty;  // rel-pos tables [L, h, D, 3]
+    const int *rel_idx;    // [M, 3]
+    float *out;
+    int accumulate;
+};
+
+// Copy one head group of a [L,h,D,3] table into shared memory as [axis][l][hh][c].
+template <int D, int HG>
+__device__ __forceinline__ void stage_table(float *dst, const float *__restrict__ src, int L, int h, int h0) {
+    const int total = 3 * L * HG * D;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int c = i % D;
+        const int hh = (i / D) % HG;
+        const int l = (i / (D * HG)) % L;
+        const int a = i / (D * HG * L);
+        dst[i] = __ldg(src + ((size_t)(l * h + h0 + hh) * D + c) * 3 + a);
+    }
+}
+
+__device__ __forceinline__ int clampi(int v, int hi) { return min(max(v, 0), hi); }
+
+// E[c..c+3] = (T[0][r0] + T[1][r1]) + T[2][r2] for one head chunk (left-to-right adds like the reference)
+template <int D, int HG>
+__device__ __forceinline__ float4 table_sum4(const float *ts, int L, int r0, int r1, int r2, int hh, int g) {
+    const float4 *t4 = reinterpret_cast<const float4 *>(ts);
+    constexpr int G = D / 4;
+    const float4 a = t4[((0 * L + r0) * HG + hh) * G + g];
+    const float4 b = t4[((1 * L + r1) * HG + hh) * G + g];
+    const float4 c = t4[((2 * L + r2) * HG + hh) * G + g];
+    return f4_add(f4_add(a, b), c);
+}
+
+// ------------------------------------------------------------------------------------------------
+// seg_dot: out[m, h] = XY ? <x,y> : 0  +  EX ? <x,Ex(m)> : 0  +  EY ? <y,Ey(m)> : 0
+//   step1 fwd            XY           x=q[n]        y=k[i1]
+//   dot_prod_with_idx v3 EX|EY        x=q[n]        y=k[i1]      Tx=table_q Ty=table_k
+//   step2-rpv bwd gattn  XY|EX        x=grad_out[n] y=v[i1]      Tx=table_v
+// A warp owns a query; its len*HG (pair, head) items are spread over 32/G lane groups of G=D/4 lanes.
+template <int D, int HG, bool XY, bool EX, bool EY>
+__global__ void __launch_bounds__(kThreads) seg_dot_kernel(const SegParams p) {
+    extern __shared__ float4 smem4[];
+    float *smem = reinterpret_cast<float *>(smem4);
+    constexpr int G = D / 4, NS = kWarp / G;
+    const int L = p.L, h = p.h, C = p.h * D;
+    const int h0 = blockIdx.y * HG;
+    const int tsz = 3 * L * HG * D;
+    float *tx = smem;
+    float *ty = tx + (EX ? tsz : 0);
+    float *xs = ty + (EY ? tsz : 0);
+    if (EX) stage_table<D, HG>(tx, p.Tx, L, h, h0);
+    if (EY) stage_table<D, HG>(ty, p.Ty, L, h, h0);
+    if (EX || EY) __syncthreads();
+
+    const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp, nwarps = blockDim.x / kWarp;
+    const int grp = lane / G, g = lane % G;
+    float4 *xw = reinterpret_cast<float4 *>(xs + warp * HG * D);
+
+    for (int base_n = blockIdx.x * kRowsPerChunk; base_n < p.N; base_n += gridDim.x * kRowsPerChunk) {
+        const int end_n = min(p.N, base_n + kRowsPerChunk);
+        for (int n = base_n + warp; n < end_n; n += nwarps) {
+            const int start = __ldg(p.offsets + n), len = __ldg(p.offsets + n + 1) - start;
+            if (len <= 0) continue;
+            __syncwarp();
+            for (int i = lane; i < HG * G; i += kWarp) xw[i] = ld_row4(p.X + (size_t)n * C + h0 * D + 4 * i);
+            __syncwarp();
+            const int items = len * HG;
+            for (int base = 0; base < items; base += NS) {
+                const int e = base + grp;
+                const bool active = e < items;
+                const int ee = active ? e : items - 1;
+                const int pair = ee / HG, hh = ee - pair * HG;
+                const int m = start + pair;
+                const int j = ld_stream(p.gather_idx + m);
+                const float4 x4 = xw[hh * G + g];
+                const float4 y4 = ld_row4(p.Y + (size_t)j * C + (h0 + hh) * D + 4 * g);
+                float acc = 0.f;
+                if (XY) acc = f4_dot(x4, y4, acc);
+                if (EX || EY) {
+                    const int r0 = clampi(ld_stream(p.rel_idx + 3 * (size_t)m + 0), L - 1);
+                    const int r1 = clampi(ld_stream(p.rel_idx + 3 * (size_t)m + 1), L - 1);
+                    const int r2 = clampi(ld_stream(p.rel_idx + 3 * (size_t)m + 2), L - 1);
+                    if (EX) acc = f4_dot(x4, table_sum4<D, HG>(tx, L, r0, r1, r2, hh, g), acc);
+                    if (EY) acc = f4_dot(y4, table_sum4<D, HG>(ty, L, r0, r1, r2, hh, g), acc);
+                }
+                acc = group_sum<G>(acc);
+                if (active && g == 0) p.out[(size_t)m * h + h0 + hh] = acc;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// seg_reduce: out[n, h, :] (+)= sum_{t in seg(n)} w[m(t), h] * ( HAS_Y ? Y[gather_idx[t], h, :] : 0  +  HAS_T ? E(m(t), h, :) : 0 )
+//   step2-rpv fwd        HAS_Y|HAS_T   w=attn  Y=v  by index1            T=table_v
+//   step1 bwd grad_q     HAS_Y         w=g     Y=k  by index1
+//   rpe  bwd grad_q      HAS_T         w=g                                T=table_q
+//   step1 bwd grad_k     HAS_Y  PERM   w=g     Y=q  by t_index0   (rows = keys, transposed CSR)
+//   rpe  bwd grad_k      HAS_T  PERM   w=g                                T=table_k
+//   step2 bwd grad_v     HAS_Y  PERM   w=attn  Y=grad_out by t_index0
+// A warp owns a row; 32/G pair slots of G lanes each accumulate float4 per head, then xor-shuffle across slots.
+template <int D, int HG, bool HAS_Y, bool HAS_T, bool PERM>
+__global__ void __launch_bounds__(kThreads) seg_reduce_kernel(const SegParams p) {
+    extern __shared__ float4 smem4[];
+    float *ts = reinterpret_cast<float *>(smem4);
+    constexpr int G = D / 4, NS = kWarp / G;
+    const int L = p.L, h = p.h, C = p.h * D;
+    const int h0 = blockIdx.y * HG;
+    if (HAS_T) {
+        stage_table<D, HG>(ts, p.Tx, L, h, h0);
+        __syncthreads();
+    }
+    const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp, nwarps = blockDim.x / kWarp;
+    const int slot = lane / G, g = lane % G;
+
+    for (int base_n = blockIdx.x * kRowsPerChunk; base_n < p.N; base_n += gridDim.x * kRowsPerChunk) {
+        const int end_n = min(p.N, base_n + kRowsPerChunk);
+        for (int n = base_n + warp; n < end_n; n += nwarps) {
+            const int start = __ldg(p.offsets + n), end = __ldg(p.offsets + n + 1);
+            float4 acc[HG];
+#pragma unroll
+            for (int hh = 0; hh < HG; ++hh) acc[hh] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int t = start + slot; t < end; t += NS) {
+                const int m = PERM ? ld_stream(p.pair_id + t) : t;
+                const int j = HAS_Y ? ld_stream(p.gather_idx + t) : 0;
+                int r0 = 0, r1 = 0, r2 = 0;
+                if (HAS_T) {
+                    r0 = clampi(ld_stream(p.rel_idx + 3 * (size_t)m + 0), L - 1);
+                    r1 = clampi(ld_stream(p.rel_idx + 3 * (size_t)m + 1), L - 1);
+                    r2 = clampi(ld_stream(p.rel_idx + 3 * (size_t)m + 2), L - 1);
+                }
+#pragma unroll
+                for (int hh = 0; hh < HG; ++hh) {
+                    const float wv = ld_stream(p.w + (size_t)m * h + h0 + hh);
+                    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (HAS_T) val = table_sum4<D, HG>(ts, L, r0, r1, r2, hh, g);
+                    if (HAS_Y) val = f4_add(val, ld_row4(p.Y + (size_t)j * C + (h0 + hh) * D + 4 * g));
+                    acc[hh] = f4_fma(wv, val, acc[hh]);
+                }
+            }
+#pragma unroll
+            for (int hh = 0; hh < HG; ++hh) {
+#pragma unroll
+                for (int o = G; o < kWarp; o <<= 1) {
+                    acc[hh].x += __shfl_xor_sync(0xffffffffu, acc[hh].x, o);
+                    acc[hh].y += __shfl_xor_sync(0xffffffffu, acc[hh].y, o);
+                    acc[hh].z += __shfl_xor_sync(0xffffffffu, acc[hh].z, o);
+                    acc[hh].w += __shfl_xor_sync(0xffffffffu, acc[hh].w, o);
+                }
+            }
+            if (slot == 0) {
+#pragma unroll
+                for (int hh = 0; hh < HG; ++hh) {
+                    float4 *dst = reinterpret_cast<float4 *>(p.out + (size_t)n * C + (h0 + hh) * D + 4 * g);
+                    *dst = p.accumulate ? f4_add(*dst, acc[hh]) : acc[hh];
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// table_grad: gT[l, h, c, a] += sum_n X[n, h, c] * W_a[n, l],  W_a[n, l] = sum_{t in seg(n), rel_idx[m(t), a] = l} w[m(t), h]
+// grid = (persistent tiles, h).  Per tile of TQ rows: phase A builds the TQ histograms in shared memory with one
+// thread per (row, axis) (private column, no atomics); phase B accumulates the outer products in registers.
+constexpr int kTQ = 64;       // rows per tile
+constexpr int kTQP = kTQ + 4; // padded row pitch of W: conflict-free LDS.128 for 8 consecutive table rows
+
+template <int D, int RPT, bool PERM>
+__global__ void __launch_bounds__(kThreads) table_grad_kernel(const SegParams p, int row_pass_base) {
+    extern __shared__ float4 smem4[];
+    constexpr int G = D / 4;
+    constexpr int NL = kThreads / G;  // threads along the (axis, l) dimension
+    const int L = p.L, h = p.h, R = 3 * L;
+    const int hh = blockIdx.y;
+    float *W = reinterpret_cast<float *>(smem4);              // [R][kTQP]
+    float4 *Xs = reinterpret_cast<float4 *>(W + R * kTQP);    // [kTQ][G]
+    const int tid = threadIdx.x;
+    const int cb = tid % G, lrow = tid / G;
+
+    float4 acc[RPT];
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int base_n = blockIdx.x * kTQ; base_n < p.N; base_n += gridDim.x * kTQ) {
+        __syncthreads();  // previous tile's phase B done
+        for (int i = tid; i < R * kTQP; i += kThreads) W[i] = 0.f;
+        for (int i = tid; i < kTQ * G; i += kThreads) {
+            const int n = base_n + i / G;
+            Xs[i] = n < p.N ? ld_row4(p.X + ((size_t)n * h + hh) * D + 4 * (i % G)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncthreads();
+        if (tid < 3 * kTQ) {
+            const int t = tid % kTQ, a = tid / kTQ;
+            const int n = base_n + t;
+            if (n < p.N) {
+                const int start = __ldg(p.offsets + n), end = __ldg(p.offsets + n + 1);
+                float *col = W + a * L * kTQP + t;
+                int i = start;
+                for (; i + 4 <= end; i += 4) {  // 4 independent load chains in flight
+                    int m[4], l[4];
+                    float wv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) m[u] = PERM ? __ldg(p.pair_id + i + u) : i + u;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        l[u] = clampi(__ldg(p.rel_idx + 3 * (size_t)m[u] + a), L - 1);
+                        wv[u] = __ldg(p.w + (size_t)m[u] * h + hh);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) col[l[u] * kTQP] += wv[u];
+                }
+                for (; i < end; ++i) {
+                    const int m = PERM ? __ldg(p.pair_id + i) : i;
+                    const int l = clampi(__ldg(p.rel_idx + 3 * (size_t)m + a), L - 1);
+                    col[l * kTQP] += __ldg(p.w + (size_t)m * h + hh);
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int t = 0; t < kTQ; t += 4) {
+            const float4 x0 = Xs[(t + 0) * G + cb], x1 = Xs[(t + 1) * G + cb];
+            const float4 x2 = Xs[(t + 2) * G + cb], x3 = Xs[(t + 3) * G + cb];
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) {
+                const int row = row_pass_base + lrow + k * NL;
+                if (row < R) {
+                    const float4 wv = *reinterpret_cast<const float4 *>(W + row * kTQP + t);
+                    acc[k] = f4_fma(wv.x, x0, acc[k]);
+                    acc[k] = f4_fma(wv.y, x1, acc[k]);
+                    acc[k] = f4_fma(wv.z, x2, acc[k]);
+                    acc[k] = f4_fma(wv.w, x3, acc[k]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+        const int row = row_pass_base + lrow + k * NL;
+        if (row < R) {
+            const int a = row / L, l = row - a * L;
+            float *dst = p.out + ((size_t)(l * h + hh) * D + 4 * cb) * 3 + a;
+            atomicAdd(dst + 0, acc[k].x);
+            atomicAdd(dst + 3, acc[k].y);
+            atomicAdd(dst + 6, acc[k].z);
+            atomicAdd(dst + 9, acc[k].w);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Segment softmax (fwd: p = softmax_seg(a + b); bwd: gs = p * (gp - <p, gp>_seg)), one warp per query.
+constexpr int kSoftCache = 4;  // values per lane kept in registers (segments up to 128 pairs in one pass)
+
+__global__ void __launch_bounds__(kThreads) segment_softmax_fwd_kernel(int N, int h, const float *__restrict__ a,
+                                                                       const float *__restrict__ b,
+                                                                       const int *__restrict__ offsets,
+                                                                       float *__restrict__ p) {
+    const int lane = threadIdx.x % kWarp;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp, nw = gridDim.x * blockDim.x / kWarp;
+    for (int n = wid; n < N; n += nw) {
+        const int start = __ldg(offsets + n), len = __ldg(offsets + n + 1) - start;
+        if (len <= 0) continue;
+        for (int hh = 0; hh < h; ++hh) {
+            const size_t base = (size_t)start * h + hh;
+            float v[kSoftCache];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int u = 0; u < kSoftCache; ++u) {
+                const int i = lane + u * kWarp;
+                v[u] = -INFINITY;
+                if (i < len) {
+                    v[u] = a[base + (size_t)i * h];
+                    if (b) v[u] += b[base + (size_t)i * h];
+                }
+                mx = fmaxf(mx, v[u]);
+            }
+            for (int i = lane + kSoftCache * kWarp; i < len; i += kWarp) {
+                float s = a[base + (size_t)i * h];
+                if (b) s += b[base + (size_t)i * h];
+                mx = fmaxf(mx, s);
+            }
+            mx = warp_max(mx);
+            float sum = 0.f;
+#pragma unroll
+            for (int u = 0; u < kSoftCache; ++u) {
+                v[u] = (lane + u * kWarp < len) ? expf(v[u] - mx) : 0.f;
+                sum += v[u];
+            }
+            for (int i = lane + kSoftCache * kWarp; i < len; i += kWarp) {
+                float s = a[base + (size_t)i * h];
+                if (b) s += b[base + (size_t)i * h];
+                sum += expf(s - mx);
+            }
+            sum = group_sum<kWarp>(sum);
+#pragma unroll
+            for (int u = 0; u < kSoftCache; ++u) {
+                const int i = lane + u * kWarp;
+                if (i < len) p[base + (size_t)i * h] = v[u] / sum;
+            }
+            for (int i = lane + kSoftCache * kWarp; i < len; i += kWarp) {
+                float s = a[base + (size_t)i * h];
+                if (b) s += b[base + (size_t)i * h];
+                p[base + (size_t)i * h] = expf(s - mx) / sum;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) segment_softmax_bwd_kernel(int N, int h, const float *__restrict__ p,
+                                                                       const float *__restrict__ gp,
+                                                                       const int *__restrict__ offsets,
+                                                                       float *__restrict__ gs) {
+    const int lane = threadIdx.x % kWarp;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp, nw = gridDim.x * blockDim.x / kWarp;
+    for (int n = wid; n < N; n += nw) {
+        const int start = __ldg(offsets + n), len = __ldg(offsets + n + 1) - start;
+        if (len <= 0) continue;
+        for (int hh = 0; hh < h; ++hh) {
+            const size_t base = (size_t)start * h + hh;
+            float dot = 0.f;
+            for (int i = lane; i < len; i += kWarp) dot = fmaf(p[base + (size_t)i * h], gp[base + (size_t)i * h], dot);
+            dot = group_sum<kWarp>(dot);
+            for (int i = lane; i < len; i += kWarp) {
+                const size_t o = base + (size_t)i * h;
+                gs[o] = p[o] * (gp[o] - dot);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side launch helpers
+static int grid_rows(int N, size_t smem, int groups) {
+    const int chunks = (N + kRowsPerChunk - 1) / kRowsPerChunk;
+    const int ctas_per_sm = (int)max((size_t)1, min((size_t)4, (size_t)(220 * 1024) / max(smem, (size_t)1)));
+    return max(1, min(chunks, (kNumSMs * ctas_per_sm + groups - 1) / groups));
+}
+
+template <typename K>
+static int prep_smem(K kernel, size_t bytes) {
+    if (bytes > 227 * 1024) {
+        set_error("shared memory request %zu B exceeds 227 KB (table too large for one head group)", bytes);
+        return STB200_ERR_ARG;
+    }
+    if (bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return STB200_ERR_CUDA;
+        }
+    }
+    return STB200_OK;
+}
+
+// heads per CTA: as many as divide h, up to 4, while the staged tables stay under ~100 KB
+static int pick_hg(int h, int D, int L, int ntables) {
+    int cap = 4;
+    while (cap > 1 && (size_t)ntables * 3 * L * cap * D * 4 > 100 * 1024) --cap;
+    return largest_head_group(h, cap);
+}
+
+template <int D, int HG, bool XY, bool EX, bool EY>
+static int launch_seg_dot_hg(const SegParams &p, cudaStream_t s) {
+    const size_t smem = ((size_t)(EX + EY) * 3 * p.L * HG * D + (kThreads / kWarp) * HG * D) * sizeof(float);
+    auto kern = seg_dot_kernel<D, HG, XY, EX, EY>;
+    if (int rc = prep_smem(kern, smem)) return rc;
+    dim3 grid(grid_rows(p.N, smem, p.h / HG), p.h / HG);
+    kern<<<grid, kThreads, smem, s>>>(p);
+    count_launch();
+    return check_launch("seg_dot");
+}
+
+template <int D, bool XY, bool EX, bool EY>
+static int launch_seg_dot_d(const SegParams &p, cudaStream_t s) {
+    switch (pick_hg(p.h, D, p.L, EX + EY)) {
+        case 4: return launch_seg_dot_hg<D, 4, XY, EX, EY>(p, s);
+        case 3: return launch_seg_dot_hg<D, 3, XY, EX, EY>(p, s);
+        case 2: return launch_seg_dot_hg<D, 2, XY, EX, EY>(p, s);
+        default: return launch_seg_dot_hg<D, 1, XY, EX, EY>(p, s);
+    }
+}
+
+template <bool XY, bool EX, bool EY>
+static int launch_seg_dot(int D, const SegParams &p, cudaStream_t s) {
+    if (p.N == 0) return STB200_OK;
+    if (D == 16) return launch_seg_dot_d<16, XY, EX, EY>(p, s);
+    return launch_seg_dot_d<32, XY, EX, EY>(p, s);
+}
+
+template <int D, int HG, bool HAS_Y, bool HAS_T, bool PERM>
+static int launch_seg_reduce_hg(const SegParams &p, cudaStream_t s) {
+    const size_t smem = (size_t)HAS_T * 3 * p.L * HG * D * sizeof(float);
+    auto kern = seg_reduce_kernel<D, HG, HAS_Y, HAS_T, PERM>;
+    if (int rc = prep_smem(kern, smem)) return rc;
+    dim3 grid(grid_rows(p.N, smem, p.h / HG), p.h / HG);
+    kern<<<grid, kThreads, smem, s>>>(p);
+    count_launch();
+    return check_launch("seg_reduce");
+}
+
+template <int D, bool HAS_Y, bool HAS_T, bool PERM>
+static int launch_seg_reduce_d(const SegParams &p, cudaStream_t s) {
+    switch (pick_hg(p.h, D, p.L, HAS_T)) {
+        case 4: return launch_seg_reduce_hg<D, 4, HAS_Y, HAS_T, PERM>(p, s);
+        case 3: return launch_seg_reduce_hg<D, 3, HAS_Y, HAS_T, PERM>(p, s);
+        case 2: return launch_seg_reduce_hg<D, 2, HAS_Y, HAS_T, PERM>(p, s);
+        default: return launch_seg_reduce_hg<D, 1, HAS_Y, HAS_T, PERM>(p, s);
+    }
+}
+
+template <bool HAS_Y, bool HAS_T, bool PERM>
+static int launch_seg_reduce(int D, const SegParams &p, cudaStream_t s) {
+    if (p.N == 0) return STB200_OK;
+    if (D == 16) return launch_seg_reduce_d<16, HAS_Y, HAS_T, PERM>(p, s);
+    return launch_seg_reduce_d<32, HAS_Y, HAS_T, PERM>(p, s);
+}
+
+template <int D, bool PERM>
+static int launch_table_grad_d(const SegParams &p, cudaStream_t s) {
+    constexpr int RPT = 4;
+    constexpr int NL = kThreads / (D / 4);
+    const int R = 3 * p.L;
+    const size_t smem = ((size_t)R * kTQP + kTQ * D) * sizeof(float);
+    auto kern = table_grad_kernel<D, RPT, PERM>;
+    if (int rc = prep_smem(kern, smem)) return rc;
+    const int tiles = (p.N + kTQ - 1) / kTQ;
+    const int ctas_per_sm = max(1, min(4, (int)((200 * 1024) / smem)));
+    const int gx = max(1, min(tiles, (kNumSMs * ctas_per_sm + p.h - 1) / p.h));
+    for (int pass = 0; pass < R; pass += NL * RPT) {
+        kern<<<dim3(gx, p.h), kThreads, smem, s>>>(p, pass);
+        count_launch();
+    }
+    return check_launch("table_grad");
+}
+
+template <bool PERM>
+static int launch_table_grad(int D, const SegParams &p, cudaStream_t s) {
+    if (p.N == 0) return STB200_OK;
+    if (D == 16) return launch_table_grad_d<16, PERM>(p, s);
+    return launch_table_grad_d<32, PERM>(p, s);
+}
+
+static int check_dims(int N, int M, int h, int D) {
+    STB200_REQUIRE(N >= 0 && M >= 0 && h > 0, STB200_ERR_ARG, "bad sizes N=%d M=%d h=%d", N, M, h);
+    STB200_REQUIRE(D == 16 || D == 32, STB200_ERR_HEAD_DIM, "d != 16 and d != 32 (got %d)", D);
+    return STB200_OK;
+}
+
+}  // namespace stb200
+
+using namespace stb200;
+
+extern "C" {
+
+int stb200_attention_step1_forward_v2(int N, int M, int h, int C, unsigned int, const float *q, const float *k,
+                                      const int *index0_offsets, const int *index1, float *attn, void *stream) {
+    STB200_REQUIRE(h > 0 && C % h == 0, STB200_ERR_ARG, "C=%d not divisible by h=%d", C, h);
+    if (int rc = check_dims(N, M, h, C / h)) return rc;
+    if (M == 0) return STB200_OK;
+    STB200_REQUIRE(q && k && index0_offsets && index1 && attn, STB200_ERR_ARG, "null pointer");
+    SegParams p{};
+    p.N = N; p.h = h; p.L = 0; p.X = q; p.Y = k; p.offsets = index0_offsets; p.gather_idx = index1; p.out = attn;
+    return launch_seg_dot<true, false, false>(C / h, p, (cudaStream_t)stream);
+}
+
+int stb200_attention_step1_backward_v2(int N, int M, int h, int C, unsigned int, const float *grad_out,
+                                       const int *index0_offsets, const int *index1, const float *q, const float *k,
+                                       float *grad_q, float *grad_k, const int *t_offsets, const int *t_pair,
+                                       const int *t_index0, void *stream) {
+    STB200_REQUIRE(h > 0 && C % h == 0, STB200_ERR_ARG, "C=%d not divisible by h=%d", C, h);
+    if (int rc = check_dims(N, M, h, C / h)) return rc;
+    STB200_REQUIRE(grad_out && index0_offsets && index1 && q && k && grad_q && grad_k, STB200_ERR_ARG, "null pointer");
+    STB200_REQUIRE(t_offsets && t_pair && t_index0, STB200_ERR_ARG, "transposed CSR required (stb200_transpose_csr)");
+    cudaStream_t s = (cudaStream_t)stream;
+    SegParams p{};
+    p.N = N; p.h = h; p.w = grad_out; p.Y = k; p.offsets = index0_offsets; p.gather_idx = index1; p.out = grad_q;
+    if (int rc = launch_seg_reduce<true, false, false>(C / h, p, s)) return rc;   // grad_q: overwritten (ref :90)
+    p.Y = q; p.offsets = t_offsets; p.gather_idx = t_index0; p.pair_id = t_pair; p.out = grad_k; p.accumulate = 1;
+    return launch_seg_reduce<true, false, true>(C / h, p, s);                     // grad_k: accumulated (ref :84)
+}
+
+int stb200_dot_prod_with_idx_forward_v3(int N, int M, int h, int hdim, int, int L, const float *q,
+                                        const int *index_q_offsets, const float *k, const int *index_k,
+                                        const float *table_q, const float *table_k, const int *rel_idx,
+                                        float *output, void *stream) {
+    if (int rc = check_dims(N, M, h, hdim)) return rc;
+    if (M == 0) return STB200_OK;
+    STB200_REQUIRE(L > 0 && q && k && index_q_offsets && index_k && table_q && table_k && rel_idx && output,
+                   STB200_ERR_ARG, "null pointer or L<=0");
+    SegParams p{};
+    p.N = N; p.h = h; p.L = L; p.X = q; p.Y = k; p.offsets = index_q_offsets; p.gather_idx = index_k;
+    p.Tx = table_q; p.Ty = table_k; p.rel_idx = rel_idx; p.out = output;
+    return launch_seg_dot<false, true, true>(hdim, p, (cudaStream_t)stream);
+}
+
+int stb200_dot_prod_with_idx_backward_v3(int N, int M, int h, int hdim, int, int L, const float *grad_out,
+                                         const float *q, const int *index_q_offsets, const float *k,
+                                         const int *index_k, const float *table_q, const float *table_k,
+                                         const int *rel_idx, float *grad_q, float *grad_k, float *grad_table_q,
+                                         float *grad_table_k, const int *t_offsets, const int *t_pair,
+                                         const int *t_index0, void *stream) {
+    if (int rc = check_dims(N, M, h, hdim)) return rc;
+    STB200_REQUIRE(L > 0 && grad_out && q && k && index_q_offsets && index_k && table_q && table_k && rel_idx &&
+                       grad_q && grad_k && grad_table_q && grad_table_k, STB200_ERR_ARG, "null pointer or L<=0");
+    STB200_REQUIRE(t_offsets && t_pair && t_index0, STB200_ERR_ARG, "transposed CSR required (stb200_transpose_csr)");
+    cudaStream_t s = (cudaStream_t)stream;
+    SegParams p{};
+    p.N = N; p.h = h; p.L = L; p.w = grad_out; p.rel_idx = rel_idx;
+    p.offsets = index_q_offsets; p.Tx = table_q; p.out = grad_q;
+    if (int rc = launch_seg_reduce<false, true, false>(hdim, p, s)) return rc;    // grad_q = sum g*Eq (overwritten, ref :338)
+    p.X = q; p.out = grad_table_q;
+    if (int rc = launch_table_grad<false>(hdim, p, s)) return rc;                 // grad_table_q (+=)
+    p.offsets = t_offsets; p.pair_id = t_pair; p.gather_idx = t_index0;
+    p.Tx = table_k; p.out = grad_k; p.accumulate = 1;
+    if (int rc = launch_seg_reduce<false, true, true>(hdim, p, s)) return rc;     // grad_k += sum g*Ek
+    p.X = k; p.out = grad_table_k;
+    return launch_table_grad<true>(hdim, p, s);                                   // grad_table_k (+=)
+}
+
+int stb200_attention_step2_with_rel_pos_value_forward_v2(int N, int M, int h, int hdim, int, int L, const float *attn,
+                                                         const float *v, const int *index0_offsets, const int *index1,
+                                                         const float *table, const int *rel_idx, float *output,
+                                                         void *stream) {
+    if (int rc = check_dims(N, M, h, hdim)) return rc;
+    STB200_REQUIRE(L > 0 && index0_offsets && output && (M == 0 || (attn && v && index1 && table && rel_idx)),
+                   STB200_ERR_ARG, "null pointer or L<=0");
+    SegParams p{};
+    p.N = N; p.h = h; p.L = L; p.w = attn; p.Y = v; p.offsets = index0_offsets; p.gather_idx = index1;
+    p.Tx = table; p.rel_idx = rel_idx; p.out = output;
+    return launch_seg_reduce<true, true, false>(hdim, p, (cudaStream_t)stream);
+}
+
+int stb200_attention_step2_with_rel_pos_value_backward_v2(int N, int M, int h, int hdim, int, int L,
+                                                          const float *grad_out, const int *index0_offsets,
+                                                          const int *index1, const float *attn, const float *v,
+                                                          const float *table, const int *rel_idx, float *grad_attn,
+                                                          float *grad_v, float *grad_table, const int *t_offsets,
+                                                          const int *t_pair, const int *t_index0, void *stream) {
+    if (int rc = check_dims(N, M, h, hdim)) return rc;
+    STB200_REQUIRE(L > 0 && grad_out && index0_offsets && index1 && attn && v && table && rel_idx && grad_attn &&
+                       grad_v && grad_table, STB200_ERR_ARG, "null pointer or L<=0");
+    STB200_REQUIRE(t_offsets && t_pair && t_index0, STB200_ERR_ARG, "transposed CSR required (stb200_transpose_csr)");
+    cudaStream_t s = (cudaStream_t)stream;
+    SegParams p{};
+    p.N = N; p.h = h; p.L = L; p.rel_idx = rel_idx;
+    p.X = grad_out; p.Y = v; p.offsets = index0_offsets; p.gather_idx = index1; p.Tx = table; p.out = grad_attn;
+    if (M > 0)
+        if (int rc = launch_seg_dot<true, true, false>(hdim, p, s)) return rc;    // grad_attn = <g, v + Ev>
+    p.w = attn; p.out = grad_table;
+    if (int rc = launch_table_grad<false>(hdim, p, s)) return rc;                 // grad_table (+=), X = grad_out
+    p.Y = grad_out; p.offsets = t_offsets; p.pair_id = t_pair; p.gather_idx = t_index0; p.out = grad_v;
+    p.accumulate = 1;
+    return launch_seg_reduce<true, false, true>(hdim, p, s);                      // grad_v += sum attn*g
+}
+
+int stb200_segment_softmax_forward(int N, int M, int h, const float *a, const float *b, const int *index0_offsets,
+                                   float *p, void *stream) {
+    STB200_REQUIRE(N >= 0 && M >= 0 && h > 0, STB200_ERR_ARG, "bad sizes");
+    if (N == 0 || M == 0) return STB200_OK;
+    STB200_REQUIRE(a && index0_offsets && p, STB200_ERR_ARG, "null pointer");
+    const int blocks = max(1, min((N + kThreads / kWarp - 1) / (kThreads / kWarp), kNumSMs * 8));
+    segment_softmax_fwd_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(N, h, a, b, index0_offsets, p);
+    count_launch();
+    return check_launch("segment_softmax_fwd");
+}
+
+int stb200_segment_softmax_backward(int N, int M, int h, const float *p, const float *grad_p,
+                                    const int *index0_offsets, float *grad_s, void *stream) {
+    STB200_REQUIRE(N >= 0 && M >= 0 && h > 0, STB200_ERR_ARG, "bad sizes");
+    if (N == 0 || M == 0) return STB200_OK;
+    STB200_REQUIRE(p && grad_p && index0_offsets && grad_s, STB200_ERR_ARG, "null pointer");
+    const int blocks = max(1, min((N + kThreads / kWarp - 1) / (kThreads / kWarp), kNumSMs * 8));
+    segment_softmax_bwd_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(N, h, p, grad_p, index0_offsets, grad_s);
+    count_launch();
+    return check_launch("segment_softmax_bwd");
+}
+
+}  // extern "C"

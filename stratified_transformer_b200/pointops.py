@@ -1,0 +1,343 @@
+"""Operator-level mirror of /root/reference/lib/pointops2/functions/pointops.py (hot-path subset).
+
+Same public names, argument orders, shapes and dtypes, so `WindowAttention`
+(model/stratified_transformer.py:164-217, model/swin3d_transformer.py:132-178) can import this module
+in place of `lib.pointops2.functions.pointops`:
+
+    attention_step1_v2(q, k, index1, index0_offsets, n_max)                                  pointops.py:203
+    dot_prod_with_idx_v3(q, index_q_offsets, n_max, k, index_k, table_q, table_k, rel_idx)  pointops.py:519
+    attention_step2_with_rel_pos_value_v2(attn, v, index0_offsets, n_max, index1, table, rel_idx)   :646
+    furthestsampling(xyz, offset, new_offset)                                                 pointops.py:31
+    attention_step1 / attention_step2 / attention_step2_v2 / dot_prod_with_idx / dot_prod_with_idx_v2 /
+    attention_step2_with_rel_pos_value                                                (v1, :140-581)
+
+plus `segment_softmax`, which replaces `attn_flat + bias` and torch_scatter's `scatter_softmax` on the path.
+
+Differences from the reference, all at the edges: inputs are validated (CUDA, dtype, contiguity) with real
+exceptions instead of asserts; `n_max` may be an int or a tensor and is never synchronised on (no launch
+shape depends on it); the ops run on torch's current stream; inputs are pinned to fp32 under autocast
+(the reference relies on call sites passing `.float()`).
+"""
+from __future__ import annotations
+
+import torch
+from torch.autograd import Function
+
+from . import pointops2_cuda as pointops_cuda
+
+
+def _n_max_int(n_max) -> int:
+    # accepted for signature compatibility; kernels ignore it, so never force a device sync on a CUDA scalar
+    if isinstance(n_max, torch.Tensor):
+        return 0
+    return int(n_max)
+
+
+def _contig(*tensors):
+    for t in tensors:
+        if not t.is_contiguous():
+            raise ValueError("pointops: all tensors must be contiguous (same contract as the reference asserts)")
+
+
+class FurthestSampling(Function):
+    @staticmethod
+    def forward(ctx, xyz, offset, new_offset):
+        """xyz (n,3) f32, offset (b) i32 cumulative, new_offset (b) i32 cumulative -> idx (m) i32."""
+        _contig(xyz)
+        offset = offset.int().contiguous()
+        new_offset = new_offset.int().contiguous()
+        b = offset.shape[0]
+        sizes = torch.diff(offset, prepend=offset.new_zeros(1))
+        host = torch.stack([sizes.max(), new_offset[b - 1]]).tolist()  # one sync, like the reference's .item()
+        idx = torch.zeros(int(host[1]), dtype=torch.int32, device=xyz.device)
+        pointops_cuda.furthestsampling_cuda(b, int(host[0]), xyz, offset, new_offset, None, idx)
+        ctx.mark_non_differentiable(idx)
+        return idx
+
+    @staticmethod
+    def backward(ctx, grad):
+        return None, None, None
+
+
+furthestsampling = FurthestSampling.apply
+
+
+class AttentionStep1_v2(Function):
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, q, k, index1, index0_offsets, n_max):
+        _contig(q, k, index0_offsets, index1)
+        N_q, h, d = q.shape
+        M = index1.shape[0]
+        out = torch.empty(M, h, dtype=torch.float32, device=q.device)
+        pointops_cuda.attention_step1_forward_cuda_v2(k.shape[0], M, h, h * d, _n_max_int(n_max), q, k,
+                                                      index0_offsets, index1, out)
+        ctx.save_for_backward(q, k, index0_offsets, index1)
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, grad_output):
+        q, k, index0_offsets, index1 = ctx.saved_tensors
+        N_q, h, d = q.shape
+        grad_output = grad_output.contiguous()
+        grad_q = torch.empty_like(q)
+        grad_k = torch.zeros_like(k)
+        pointops_cuda.attention_step1_backward_cuda_v2(N_q, index1.shape[0], h, h * d, 0, grad_output,
+                                                       index0_offsets, index1, q, k, grad_q, grad_k)
+        return grad_q, grad_k, None, None, None
+
+
+attention_step1_v2 = AttentionStep1_v2.apply
+
+
+class DotProdWithIdx_v3(Function):
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, q, index_q_offsets, n_max, k, index_k, table_q, table_k, rel_idx):
+        _contig(q, index_q_offsets, k, index_k, table_q, table_k, rel_idx)
+        N, h, hdim = q.shape
+        M = index_k.shape[0]
+        if table_k.shape[0] != table_q.shape[0]:
+            raise ValueError("table_q and table_k must have the same length")
+        out = torch.empty(M, h, dtype=torch.float32, device=q.device)
+        pointops_cuda.dot_prod_with_idx_forward_cuda_v3(N, M, h, hdim, _n_max_int(n_max), q, index_q_offsets, k,
+                                                        index_k, table_q, table_k, rel_idx, out)
+        ctx.save_for_backward(q, index_q_offsets, k, index_k, table_q, table_k, rel_idx)
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, grad_output):
+        q, index_q_offsets, k, index_k, table_q, table_k, rel_idx = ctx.saved_tensors
+        N, h, hdim = q.shape
+        grad_output = grad_output.contiguous()
+        grad_q = torch.empty_like(q)
+        grad_k = torch.zeros_like(k)
+        grad_tq = torch.zeros_like(table_q)
+        grad_tk = torch.zeros_like(table_k)
+        pointops_cuda.dot_prod_with_idx_backward_cuda_v3(N, index_k.shape[0], h, hdim, 0, grad_output, q,
+                                                         index_q_offsets, k, index_k, table_q, table_k, rel_idx,
+                                                         grad_q, grad_k, grad_tq, grad_tk)
+        return grad_q, None, None, grad_k, None, grad_tq, grad_tk, None
+
+
+dot_prod_with_idx_v3 = DotProdWithIdx_v3.apply
+
+
+class AttentionStep2WithRelPosValue_v2(Function):
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, attn, v, index0_offsets, n_max, index1, table, rel_idx):
+        _contig(attn, v, index0_offsets, index1, table, rel_idx)
+        M, h = attn.shape
+        N, _, hdim = v.shape
+        out = torch.empty(N, h, hdim, dtype=torch.float32, device=v.device)
+        pointops_cuda.attention_step2_with_rel_pos_value_forward_cuda_v2(N, M, h, hdim, _n_max_int(n_max), attn, v,
+                                                                         index0_offsets, index1, table, rel_idx, out)
+        ctx.save_for_backward(attn, v, index0_offsets, index1, table, rel_idx)
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, grad_output):
+        attn, v, index0_offsets, index1, table, rel_idx = ctx.saved_tensors
+        M, h = attn.shape
+        N, _, hdim = v.shape
+        grad_output = grad_output.contiguous()
+        grad_attn = torch.empty_like(attn)
+        grad_v = torch.zeros_like(v)
+        grad_table = torch.zeros_like(table)
+        pointops_cuda.attention_step2_with_rel_pos_value_backward_cuda_v2(N, M, h, hdim, 0, grad_output,
+                                                                          index0_offsets, index1, attn, v, table,
+                                                                          rel_idx, grad_attn, grad_v, grad_table)
+        return grad_attn, grad_v, None, None, None, grad_table, None
+
+
+attention_step2_with_rel_pos_value_v2 = AttentionStep2WithRelPosValue_v2.apply
+
+
+class SegmentSoftmax(Function):
+    """p = softmax over each query's pairs of (a + b), per head.  Replaces
+    `attn_flat + relative_position_bias` + `scatter_softmax(src, index_0, dim=0)`
+    (model/stratified_transformer.py:203,205) with one kernel keyed by the CSR offsets."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, a, b, index0_offsets):
+        _contig(a, index0_offsets)
+        if b is not None:
+            _contig(b)
+        M, h = a.shape
+        N = index0_offsets.shape[0] - 1
+        p = torch.empty_like(a)
+        pointops_cuda.segment_softmax_forward_cuda(N, M, h, a, b, index0_offsets, p)
+        ctx.save_for_backward(p, index0_offsets)
+        ctx.has_b = b is not None
+        return p
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, grad_p):
+        p, index0_offsets = ctx.saved_tensors
+        M, h = p.shape
+        grad_s = torch.empty_like(p)
+        pointops_cuda.segment_softmax_backward_cuda(index0_offsets.shape[0] - 1, M, h, p, grad_p.contiguous(),
+                                                    index0_offsets, grad_s)
+        return grad_s, (grad_s if ctx.has_b else None), None
+
+
+def segment_softmax(a, index0_offsets, b=None):
+    return SegmentSoftmax.apply(a, b, index0_offsets)
+
+
+def scatter_softmax(src, index, dim=0):
+    """Drop-in for torch_scatter.scatter_softmax as the reference calls it (sorted `index`, dim 0)."""
+    if dim != 0 or src.dim() != 2:
+        raise NotImplementedError("scatter_softmax shim: only src [M,h], dim=0 (the reference's call) is supported")
+    n = int(index[-1].item()) + 1 if index.numel() else 0
+    counts = torch.bincount(index, minlength=n)
+    offsets = torch.cat([counts.new_zeros(1), counts.cumsum(0)]).int()
+    return SegmentSoftmax.apply(src.contiguous(), None, offsets)
+
+
+# ------------------------------------------------------------------------------------------------ v1 family
+class AttentionStep1(Function):
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, q, k, index0, index1):
+        _contig(q, k, index0, index1)
+        N_q, h, d = q.shape
+        M = index0.shape[0]
+        out = torch.zeros(M, h, dtype=torch.float32, device=q.device)
+        pointops_cuda.attention_step1_forward_cuda(k.shape[0], M, h, h * d, q, k, index0, index1, out)
+        ctx.save_for_backward(q, k, index0, index1)
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, grad_output):
+        q, k, index0, index1 = ctx.saved_tensors
+        N_q, h, d = q.shape
+        grad_q, grad_k = torch.zeros_like(q), torch.zeros_like(k)
+        pointops_cuda.attention_step1_backward_cuda(N_q, index0.shape[0], h, h * d, grad_output.contiguous(), index0,
+                                                    index1, q, k, grad_q, grad_k)
+        return grad_q, grad_k, None, None
+
+
+attention_step1 = AttentionStep1.apply
+
+
+class AttentionStep2(Function):
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, attn, v, index0, index1):
+        _contig(attn, v, index0, index1)
+        M, h = attn.shape
+        N_q = int(index0.max().item()) + 1
+        _, _, d = v.shape
+        out = torch.zeros(N_q, h, d, dtype=torch.float32, device=v.device)
+        pointops_cuda.attention_step2_forward_cuda(N_q, M, h, h * d, attn, v, index0, index1, out)
+        ctx.save_for_backward(attn, v, index0, index1)
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, grad_output):
+        attn, v, index0, index1 = ctx.saved_tensors
+        N_q, h, d = grad_output.shape
+        grad_attn, grad_v = torch.zeros_like(attn), torch.zeros_like(v)
+        pointops_cuda.attention_step2_backward_cuda(N_q, attn.shape[0], h, h * d, grad_output.contiguous(), index0,
+                                                    index1, attn, v, grad_attn, grad_v)
+        return grad_attn, grad_v, None, None
+
+
+attention_step2 = AttentionStep2.apply
+attention_step2_v2 = AttentionStep2.apply  # the reference's AttentionStep2_v2 calls the same v1 symbols (pointops.py:284)
+
+
+class DotProdWithIdx(Function):
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, q, index, table, rel_idx):
+        _contig(q, index, table, rel_idx)
+        N, h, hdim = q.shape
+        M = index.shape[0]
+        out = torch.zeros(M, h, dtype=torch.float32, device=q.device)
+        pointops_cuda.dot_prod_with_idx_forward_cuda(N, M, h, hdim, q, index, table, rel_idx, out)
+        ctx.save_for_backward(q, index, table, rel_idx)
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, grad_output):
+        q, index, table, rel_idx = ctx.saved_tensors
+        N, h, hdim = q.shape
+        grad_q, grad_table = torch.zeros_like(q), torch.zeros_like(table)
+        pointops_cuda.dot_prod_with_idx_backward_cuda(N, index.shape[0], h, hdim, grad_output.contiguous(), q, index,
+                                                      table, rel_idx, grad_q, grad_table)
+        return grad_q, None, grad_table, None
+
+
+dot_prod_with_idx = DotProdWithIdx.apply
+
+
+class DotProdWithIdx_v2(Function):
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, q, index_q, k, index_k, table_q, table_k, rel_idx):
+        _contig(q, index_q, k, index_k, table_q, table_k, rel_idx)
+        N, h, hdim = q.shape
+        M = index_q.shape[0]
+        out = torch.zeros(M, h, dtype=torch.float32, device=q.device)
+        # the reference pre-sorts pairs by merged rel idx here (pointops.py:386-393); the result does not
+        # depend on that order, so the sort is skipped
+        pointops_cuda.dot_prod_with_idx_forward_cuda_v2(N, M, h, hdim, 0, 0, q, index_q, k, index_k, table_q,
+                                                        table_k, rel_idx, None, None, out)
+        ctx.save_for_backward(q, index_q, k, index_k, table_q, table_k, rel_idx)
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, grad_output):
+        q, index_q, k, index_k, table_q, table_k, rel_idx = ctx.saved_tensors
+        N, h, hdim = q.shape
+        grad_q, grad_k = torch.zeros_like(q), torch.zeros_like(k)
+        grad_tq, grad_tk = torch.zeros_like(table_q), torch.zeros_like(table_k)
+        pointops_cuda.dot_prod_with_idx_backward_cuda_v2(N, index_q.shape[0], h, hdim, 0, 0, grad_output.contiguous(),
+                                                         q, index_q, k, index_k, table_q, table_k, rel_idx, None,
+                                                         None, grad_q, grad_k, grad_tq, grad_tk)
+        return grad_q, None, grad_k, None, grad_tq, grad_tk, None
+
+
+dot_prod_with_idx_v2 = DotProdWithIdx_v2.apply
+
+
+class AttentionStep2WithRelPosValue(Function):
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, attn, v, index0, index1, table, rel_idx):
+        _contig(attn, v, index0, index1, table, rel_idx)
+        M, h = attn.shape
+        _, _, hdim = v.shape
+        N_q = int(index0.max().item()) + 1
+        out = torch.zeros(N_q, h, hdim, dtype=torch.float32, device=v.device)
+        pointops_cuda.attention_step2_with_rel_pos_value_forward_cuda(N_q, M, h, hdim, attn, v, index0, index1,
+                                                                      table, rel_idx, out)
+        ctx.save_for_backward(attn, v, index0, index1, table, rel_idx)
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, grad_output):
+        attn, v, index0, index1, table, rel_idx = ctx.saved_tensors
+        N_q, h, hdim = grad_output.shape
+        grad_attn, grad_v, grad_table = torch.zeros_like(attn), torch.zeros_like(v), torch.zeros_like(table)
+        pointops_cuda.attention_step2_with_rel_pos_value_backward_cuda(N_q, attn.shape[0], h, hdim,
+                                                                       grad_output.contiguous(), index0, index1, attn,
+                                                                       v, table, rel_idx, grad_attn, grad_v,
+                                                                       grad_table)
+        return grad_attn, grad_v, None, None, grad_table, None
+
+
+attention_step2_with_rel_pos_value = AttentionStep2WithRelPosValue.apply

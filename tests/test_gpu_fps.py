@@ -1,0 +1,58 @@
+"""Exact FPS (-m gpu): the cluster kernel must return bit-identical indices to the C oracle
+(oracle/fps_oracle.c) and to the reference kernel itself (oracle/_ref), including tie-heavy
+lattice-aligned scenes and every code path (single CTA, cluster, several points per thread)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fps_oracle, index_oracle as io, ref_cuda
+
+pytestmark = pytest.mark.gpu
+
+
+def ours(xyz, offset, new_offset):
+    from stratified_transformer_b200 import pointops
+    idx = pointops.furthestsampling(torch.from_numpy(xyz).cuda(), torch.from_numpy(offset).cuda(),
+                                    torch.from_numpy(new_offset).cuda())
+    torch.cuda.synchronize()
+    return idx.cpu().numpy()
+
+
+def scene(n, seed, lattice=False, extent=(6.0, 5.0, 3.0)):
+    rng = np.random.default_rng(seed)
+    pts = rng.uniform(0, 1, (n, 3)) * np.asarray(extent)
+    if lattice:
+        pts = np.round(pts / 0.04) * 0.04
+    return pts.astype(np.float32)
+
+
+@pytest.mark.parametrize("sizes,ds,lattice", [
+    ([700], 8, False),                 # B = 512 < 1024, single CTA
+    ([1000, 333, 1024], 4, False),     # ragged batch, mixed sizes
+    ([5000, 4100], 8, False),          # cluster path
+    ([3000, 2500], 8, True),           # exact distance ties everywhere
+    ([20001, 19999, 20000], 8, False), # S3DIS layer-1 sizes
+    ([1], 8, False), ([2, 5], 1, False),
+])
+def test_fps_exact_vs_oracle_and_reference(sizes, ds, lattice):
+    xyz = np.concatenate([scene(n, 10 + i, lattice) for i, n in enumerate(sizes)])
+    offset = np.cumsum(sizes).astype(np.int32)
+    new_offset = io.fps_new_offset(offset, ds)
+    want = fps_oracle.furthestsampling(xyz, offset, new_offset)
+    got = ours(xyz, offset, new_offset)
+    assert np.array_equal(got, want)
+    if ref_cuda.available():
+        ref = ref_cuda.furthestsampling(torch.from_numpy(xyz).cuda(), torch.from_numpy(offset).cuda(),
+                                        torch.from_numpy(new_offset).cuda()).cpu().numpy()
+        assert np.array_equal(ref, want), "oracle disagrees with the reference kernel"
+
+
+def test_fps_full_size_scene():
+    """BASELINE cfg2 scene size: 80k points, 10 001 samples; oracle takes ~2 s."""
+    from stratified_transformer_b200.synthetic import make_scene
+    xyz, _ = make_scene(0, 80000)
+    offset = np.array([80000], np.int32)
+    new_offset = io.fps_new_offset(offset, 8)
+    want = fps_oracle.furthestsampling(xyz, offset, new_offset)
+    got = ours(xyz, offset, new_offset)
+    assert np.array_equal(got, want)

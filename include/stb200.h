@@ -145,6 +145,38 @@ int stb200_attention_step2_with_rel_pos_value_backward(int N, int M, int h, int 
 int stb200_furthestsampling(int b, int n, const float *xyz, const int *offset, const int *new_offset,
                             float *tmp, int *idx, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Pair-index construction (new: the reference does this in Python with torch ops + torch_geometric's
+ * voxel_grid, model/stratified_transformer.py:10-65, 267-317).  Two calls because the caller allocates
+ * index_1 / rel_idx and therefore has to learn M in between:
+ *
+ *   1. stb200_stratified_pairs_count: window partition for one block parity (0: unshifted, 1: shifted by
+ *      w/2), sampled keys from `downsample_idx` (m = 0 -> dense pairs only, the Swin variant), per-query
+ *      key counts -> index0_offsets [N+1] and totals[4] = {M, n_max, error flag, 0} (device memory).
+ *      Intermediate state stays in `workspace` (stb200_pair_builder_workspace_bytes(N) bytes).
+ *   2. stb200_stratified_pairs_fill: emits index_1 [M] (per query: dense keys ascending by point id, then
+ *      sparse keys ascending by point id), rel_idx [M,3] (may be NULL) and index_0 [M] (may be NULL) from the
+ *      same workspace.  window_size_x2 = (float)(2.0 * window_size), quant_size as fp32 — the scalars of
+ *      model/stratified_transformer.py:188.
+ * offset: cumulative point counts per scene [b] (int32), xyz [N,3] fp32. */
+size_t stb200_pair_builder_workspace_bytes(int N);
+int stb200_stratified_pairs_count(int N, int b, const float *xyz, const int *offset, float window_size, int parity,
+                                  const int *downsample_idx, int m, void *workspace, size_t workspace_bytes,
+                                  int *index0_offsets, int *totals, void *stream);
+int stb200_stratified_pairs_fill(int N, const float *xyz, float window_size_x2, float quant_size, int has_sparse,
+                                 void *workspace, size_t workspace_bytes, const int *index0_offsets, int *index_1,
+                                 int *rel_idx, int *index_0, void *stream);
+
+/* Relative-position index of an existing CSR pair list.
+ * Stratified: idx = ((round((xyz[i0]-xyz[i1])*1e5)/1e5) + 2w - 1e-4) // quant  (stratified_transformer.py:186-188)
+ * Swin:       xq = ((xyz - min + shift) % w) // quant; idx = xq[i0] - xq[i1] + qgl - 1 (swin3d_transformer.py:151-154)
+ * both with torch's fp32 semantics (round-half-even, fmod-based floor division). */
+int stb200_rel_pos_index_stratified(int N, const float *xyz, const int *index0_offsets, const int *index_1,
+                                    float window_size_x2, float quant_size, int *rel_idx, void *stream);
+int stb200_rel_pos_index_swin(int N, const float *xyz, const int *index0_offsets, const int *index_1,
+                              float window_size, float quant_size, float shift_size, int quant_grid_length,
+                              float *xq_scratch, unsigned *mm_scratch, int *rel_idx, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

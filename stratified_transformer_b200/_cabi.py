@@ -34,12 +34,17 @@ _SIGNATURES = {
     "stb200_attention_step2_with_rel_pos_value_forward": [_c_int] * 5 + [P] * 8,
     "stb200_attention_step2_with_rel_pos_value_backward": [_c_int] * 5 + [P] * 11,
     "stb200_furthestsampling": [_c_int, _c_int] + [P] * 6,
+    "stb200_stratified_pairs_count": [_c_int, _c_int, P, P, ctypes.c_float, _c_int, P, _c_int, P, _c_size_t, P, P, P],
+    "stb200_stratified_pairs_fill": [_c_int, P, ctypes.c_float, ctypes.c_float, _c_int, P, _c_size_t, P, P, P, P, P],
+    "stb200_rel_pos_index_stratified": [_c_int, P, P, P, ctypes.c_float, ctypes.c_float, P, P],
+    "stb200_rel_pos_index_swin": [_c_int, P, P, P, ctypes.c_float, ctypes.c_float, ctypes.c_float, _c_int, P, P, P, P],
 }
 _RESTYPES = {
     "stb200_last_error": (ctypes.c_char_p, []),
     "stb200_launch_count": (ctypes.c_longlong, []),
     "stb200_version": (_c_int, []),
     "stb200_transpose_csr_workspace_bytes": (_c_size_t, [_c_int, _c_int]),
+    "stb200_pair_builder_workspace_bytes": (_c_size_t, [_c_int]),
 }
 
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + list(_RESTYPES))

@@ -1,0 +1,473 @@
+// Pair-index construction for stratified window attention, entirely on the device.
+//
+// Specification = the reference's Python (paths under /root/reference):
+//   model/stratified_transformer.py:44-65    grid_sample  (voxel_grid -> unique -> p2v_map)
+//   model/stratified_transformer.py:10-42    get_indice_pairs (dense pairs per small window; sparse pairs =
+//                                            FPS-sampled keys of the 2x window whose window_coord differs)
+//   model/stratified_transformer.py:311-317  sort by query, bincount, cumsum -> CSR
+//   model/stratified_transformer.py:186-188  relative position index
+//   torch_geometric voxel_grid (third party) restated in SURVEY Appendix B.2
+// Output order inside a query segment is the canonical one (dense keys ascending by point id, then sparse keys
+// ascending by point id); the reference's own order is unspecified because it uses unstable sorts.
+//
+// The reference materialises [n,k,k] boolean masks and an [n,k,k,3] coordinate compare per block and sorts M
+// 64-bit pair ids.  Here: two N-element radix sorts group the points by small / large window, sampled points
+// are compacted per large window, then one warp per query counts and (after a scan) emits its keys and the
+// rel-pos indices in a single pass.  Nothing M-sized is ever sorted.
+//
+// fp32 arithmetic that decides integers is reproduced operation by operation with rounding-explicit
+// intrinsics (no contraction): voxel ids use truncating division, window_coord and the rel-pos index use
+// torch's fmod-based floor division (c10/util/generic_math.h div_floor_floating).
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace stb200 {
+
+// ---- exact fp32 helpers ------------------------------------------------------------------------------
+__device__ __forceinline__ float floor_div_f32(float a, float b) {  // torch `a // b`
+    if (b == 0.f) return __fdiv_rn(a, b);
+    const float mod = fmodf(a, b);
+    float div = __fdiv_rn(__fsub_rn(a, mod), b);
+    if (mod != 0.f && ((b < 0.f) != (mod < 0.f))) div = __fsub_rn(div, 1.f);
+    if (div != 0.f) {
+        float fl = floorf(div);
+        if (__fsub_rn(div, fl) > 0.5f) fl = __fadd_rn(fl, 1.f);
+        return fl;
+    }
+    return copysignf(0.f, __fdiv_rn(a, b));
+}
+
+__device__ __forceinline__ float remainder_f32(float a, float b) {  // torch `a % b`
+    float mod = fmodf(a, b);
+    if (mod != 0.f && ((b < 0.f) != (mod < 0.f))) mod = __fadd_rn(mod, b);
+    return mod;
+}
+
+__device__ __forceinline__ int rel_index_stratified(float xa, float xb, float two_w, float quant) {
+    float r = __fsub_rn(xa, xb);
+    r = __fdiv_rn(rintf(__fmul_rn(r, 100000.f)), 100000.f);
+    const float t = __fsub_rn(__fadd_rn(r, two_w), 0.0001f);
+    return (int)floor_div_f32(t, quant);
+}
+
+__device__ __forceinline__ unsigned f2ord(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+
+// ---- builder state (lives in the caller's workspace) ---------------------------------------------------
+struct GridParams {       // written by params_kernel
+    float mn[3], mx[3];   // global min / max of xyz over the whole batch
+    float start[3];       // voxel_grid start (== mn for both parities)
+    float shift_s, shift_l, size_s, size_l;
+    long long stride_s[4], stride_l[4];
+    int err;              // 1: more than 2^32 voxels
+    int M, n_max;
+};
+
+struct BuilderState {
+    GridParams *gp;
+    unsigned *mm;                 // ordered-uint min[3], max[3]
+    unsigned *key_s, *key_l, *skey_s, *skey_l;
+    int *iota, *order_s, *order_l;
+    int *flag_s, *flag_l, *rank_s, *rank_l;   // rank = inclusive scan of flags
+    int *wstart_s, *wstart_l;     // [N+1] window start positions in order_*
+    int *win_s, *win_l;           // window rank of each point
+    int *sflag, *spos;            // [N+1] sampled flag over order_l positions and its exclusive scan
+    int *samp;                    // sampled points grouped by large window
+    unsigned char *ds_mask;       // [N]
+    int4 *wc;                     // window_coord per point (x,y,z,unused)
+    int *counts;                  // [N+1]
+    void *cub_tmp;
+    size_t cub_bytes;
+};
+
+static size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static size_t cub_temp_bytes(int N) {
+    size_t a = 0, b = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, (const unsigned *)nullptr, (unsigned *)nullptr, (const int *)nullptr,
+                                    (int *)nullptr, N, 0, 32);
+    cub::DeviceScan::InclusiveSum(nullptr, b, (const int *)nullptr, (int *)nullptr, N + 1);
+    return a > b ? a : b;
+}
+
+static size_t carve(BuilderState &st, char *base, int N) {
+    size_t o = 0;
+    auto take = [&](size_t bytes) { char *p = base ? base + o : nullptr; o += al(bytes); return p; };
+    const size_t ni = (size_t)(N + 1) * sizeof(int);
+    st.gp = (GridParams *)take(sizeof(GridParams));
+    st.mm = (unsigned *)take(6 * sizeof(unsigned));
+    st.key_s = (unsigned *)take(ni); st.key_l = (unsigned *)take(ni);
+    st.skey_s = (unsigned *)take(ni); st.skey_l = (unsigned *)take(ni);
+    st.iota = (int *)take(ni); st.order_s = (int *)take(ni); st.order_l = (int *)take(ni);
+    st.flag_s = (int *)take(ni); st.flag_l = (int *)take(ni); st.rank_s = (int *)take(ni); st.rank_l = (int *)take(ni);
+    st.wstart_s = (int *)take(ni); st.wstart_l = (int *)take(ni);
+    st.win_s = (int *)take(ni); st.win_l = (int *)take(ni);
+    st.sflag = (int *)take(ni); st.spos = (int *)take(ni); st.samp = (int *)take(ni);
+    st.ds_mask = (unsigned char *)take((size_t)N + 1);
+    st.wc = (int4 *)take((size_t)(N + 1) * sizeof(int4));
+    st.counts = (int *)take(ni);
+    st.cub_bytes = cub_temp_bytes(N);
+    st.cub_tmp = take(st.cub_bytes);
+    return o + 256;
+}
+
+// ---- kernels -------------------------------------------------------------------------------------------
+__global__ void init_state_kernel(unsigned *mm, GridParams *gp, unsigned char *ds_mask, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 3) mm[i] = 0xffffffffu;
+    else if (i < 6) mm[i] = 0u;
+    if (i == 0) { gp->err = 0; gp->M = 0; gp->n_max = 0; }
+    for (int j = i; j < N; j += gridDim.x * blockDim.x) ds_mask[j] = 0;
+}
+
+__global__ void minmax_kernel(int N, const float *__restrict__ xyz, unsigned *mm) {
+    unsigned lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0u, 0u, 0u};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const unsigned u = f2ord(__ldg(xyz + (size_t)i * 3 + a));
+            lo[a] = min(lo[a], u);
+            hi[a] = max(hi[a], u);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        lo[a] = __reduce_min_sync(0xffffffffu, lo[a]);
+        hi[a] = __reduce_max_sync(0xffffffffu, hi[a]);
+    }
+    if (threadIdx.x % kWarp == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            atomicMin(mm + a, lo[a]);
+            atomicMax(mm + 3 + a, hi[a]);
+        }
+    }
+}
+
+__global__ void mark_sampled_kernel(int m, const int *__restrict__ ds_idx, unsigned char *ds_mask, int N) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        const int p = __ldg(ds_idx + i);
+        if (p >= 0 && p < N) ds_mask[p] = 1;
+    }
+}
+
+// voxel_grid strides: k_{d+1} = k_d * (trunc((end_d - start_d) / size_d) + 1); 4th coordinate = batch id, size 1
+__global__ void params_kernel(const unsigned *mm, GridParams *gp, float w, int parity, int b) {
+    if (threadIdx.x || blockIdx.x) return;
+    for (int a = 0; a < 3; ++a) {
+        gp->mn[a] = ord2f(mm[a]);
+        gp->mx[a] = ord2f(mm[3 + a]);
+        gp->start[a] = gp->mn[a];
+    }
+    const float w2 = __fmul_rn(2.f, w);
+    gp->size_s = w;
+    gp->size_l = w2;
+    gp->shift_s = parity ? __fmul_rn(0.5f, w) : 0.f;
+    gp->shift_l = parity ? __fmul_rn(0.5f, w2) : 0.f;
+    for (int which = 0; which < 2; ++which) {
+        const float size = which ? w2 : w, shift = which ? gp->shift_l : gp->shift_s;
+        long long *stride = which ? gp->stride_l : gp->stride_s;
+        long long k = 1;
+        for (int a = 0; a < 3; ++a) {
+            stride[a] = k;
+            const float end = parity ? __fadd_rn(gp->mx[a], shift) : gp->mx[a];
+            k *= (long long)__fdiv_rn(__fsub_rn(end, gp->start[a]), size) + 1;
+        }
+        stride[3] = k;
+        k *= (long long)(b - 1) + 1;
+        if (k >= (1LL << 32) || k <= 0) gp->err = 1;
+    }
+}
+
+__global__ void keys_kernel(int N, int b, const float *__restrict__ xyz, const int *__restrict__ offset,
+                            const GridParams *__restrict__ gp, int parity, unsigned *key_s, unsigned *key_l, int *iota,
+                            int4 *wc) {
+    const GridParams g = *gp;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        int lo = 0, hi = b - 1;  // batch id = first scene whose cumulative offset exceeds i
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(offset + mid) > i) hi = mid; else lo = mid + 1;
+        }
+        long long ks = (long long)lo * g.stride_s[3], kl = (long long)lo * g.stride_l[3];
+        int4 c = make_int4(0, 0, 0, 0);
+        int *cp = &c.x;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float x = __ldg(xyz + (size_t)i * 3 + a);
+            const float ps = parity ? __fadd_rn(x, g.shift_s) : x, pl = parity ? __fadd_rn(x, g.shift_l) : x;
+            ks += (long long)__fdiv_rn(__fsub_rn(ps, g.start[a]), g.size_s) * g.stride_s[a];
+            kl += (long long)__fdiv_rn(__fsub_rn(pl, g.start[a]), g.size_l) * g.stride_l[a];
+            // window_coord (get_indice_pairs): (xyz [+ w/2] - xyz_min) // w with torch's floor division
+            cp[a] = (int)floor_div_f32(__fsub_rn(ps, g.mn[a]), g.size_s);
+        }
+        key_s[i] = (unsigned)ks;
+        key_l[i] = (unsigned)kl;
+        iota[i] = i;
+        wc[i] = c;
+    }
+}
+
+__global__ void flags_kernel(int N, const unsigned *__restrict__ sk_s, const unsigned *__restrict__ sk_l,
+                             const int *__restrict__ order_l, const unsigned char *__restrict__ ds_mask, int *flag_s,
+                             int *flag_l, int *sflag) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= N; i += gridDim.x * blockDim.x) {
+        if (i == N) {
+            flag_s[i] = flag_l[i] = sflag[i] = 0;
+        } else {
+            flag_s[i] = i == 0 || sk_s[i] != sk_s[i - 1];
+            flag_l[i] = i == 0 || sk_l[i] != sk_l[i - 1];
+            sflag[i] = ds_mask[order_l[i]];
+        }
+    }
+}
+
+__global__ void scatter_windows_kernel(int N, const int *__restrict__ order_s, const int *__restrict__ order_l,
+                                       const int *__restrict__ flag_s, const int *__restrict__ flag_l,
+                                       const int *__restrict__ rank_s, const int *__restrict__ rank_l,
+                                       const int *__restrict__ sflag, const int *__restrict__ spos, int *wstart_s,
+                                       int *wstart_l, int *win_s, int *win_l, int *samp) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        const int rs = rank_s[i] - 1, rl = rank_l[i] - 1;
+        win_s[order_s[i]] = rs;
+        win_l[order_l[i]] = rl;
+        if (flag_s[i]) wstart_s[rs] = i;
+        if (flag_l[i]) wstart_l[rl] = i;
+        if (i == N - 1) {
+            wstart_s[rs + 1] = N;
+            wstart_l[rl + 1] = N;
+        }
+        if (sflag[i]) samp[spos[i]] = order_l[i];
+    }
+}
+
+__device__ __forceinline__ bool wc_differs(int4 a, int4 b) { return a.x != b.x || a.y != b.y || a.z != b.z; }
+
+// one warp per query: number of keys = |small window| + #{sampled b in large window : wc(a) != wc(b)}
+__global__ void count_pairs_kernel(int N, const int *__restrict__ win_s, const int *__restrict__ win_l,
+                                   const int *__restrict__ wstart_s, const int *__restrict__ wstart_l,
+                                   const int *__restrict__ spos, const int *__restrict__ samp,
+                                   const int4 *__restrict__ wc, int *counts, GridParams *gp, int has_sparse) {
+    const int lane = threadIdx.x % kWarp;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp, nw = gridDim.x * blockDim.x / kWarp;
+    int local_max = 0;
+    for (int a = wid; a < N; a += nw) {
+        const int ws = win_s[a];
+        int cnt = wstart_s[ws + 1] - wstart_s[ws];
+        if (has_sparse) {
+            const int wl = win_l[a];
+            const int s0 = spos[wstart_l[wl]], s1 = spos[wstart_l[wl + 1]];
+            const int4 ca = wc[a];
+            int sparse = 0;
+            for (int s = s0 + lane; s < s1; s += kWarp) sparse += wc_differs(ca, wc[samp[s]]);
+            cnt += __reduce_add_sync(0xffffffffu, sparse);
+        }
+        if (lane == 0) counts[a] = cnt;
+        local_max = max(local_max, cnt);
+    }
+    if (lane == 0) {
+        if (wid == 0) counts[N] = 0;
+        atomicMax(&gp->n_max, local_max);
+    }
+}
+
+__global__ void finish_count_kernel(int N, const int *__restrict__ offsets, GridParams *gp, int *totals) {
+    if (threadIdx.x || blockIdx.x) return;
+    gp->M = offsets[N];
+    totals[0] = offsets[N];
+    totals[1] = gp->n_max;
+    totals[2] = gp->err;
+    totals[3] = 0;
+}
+
+// one warp per query: emit keys (dense ascending id, then sparse ascending id) + rel-pos index (+ index_0)
+__global__ void fill_pairs_kernel(int N, const float *__restrict__ xyz, const int *__restrict__ offsets,
+                                  const int *__restrict__ win_s, const int *__restrict__ win_l,
+                                  const int *__restrict__ wstart_s, const int *__restrict__ wstart_l,
+                                  const int *__restrict__ order_s, const int *__restrict__ spos,
+                                  const int *__restrict__ samp, const int4 *__restrict__ wc, int has_sparse,
+                                  float two_w, float quant, int *__restrict__ index_1, int *__restrict__ rel_idx,
+                                  int *__restrict__ index_0) {
+    const int lane = threadIdx.x % kWarp;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp, nw = gridDim.x * blockDim.x / kWarp;
+    for (int a = wid; a < N; a += nw) {
+        const float xa = __ldg(xyz + (size_t)a * 3), ya = __ldg(xyz + (size_t)a * 3 + 1), za = __ldg(xyz + (size_t)a * 3 + 2);
+        int out = offsets[a];
+        auto emit = [&](int pos, int b) {
+            index_1[pos] = b;
+            if (index_0) index_0[pos] = a;
+            if (rel_idx) {
+                const float xb = __ldg(xyz + (size_t)b * 3), yb = __ldg(xyz + (size_t)b * 3 + 1), zb = __ldg(xyz + (size_t)b * 3 + 2);
+                rel_idx[(size_t)pos * 3 + 0] = rel_index_stratified(xa, xb, two_w, quant);
+                rel_idx[(size_t)pos * 3 + 1] = rel_index_stratified(ya, yb, two_w, quant);
+                rel_idx[(size_t)pos * 3 + 2] = rel_index_stratified(za, zb, two_w, quant);
+            }
+        };
+        const int ws = win_s[a];
+        const int d0 = wstart_s[ws], d1 = wstart_s[ws + 1];
+        for (int i = d0 + lane; i < d1; i += kWarp) emit(out + (i - d0), order_s[i]);
+        out += d1 - d0;
+        if (has_sparse) {
+            const int wl = win_l[a];
+            const int s0 = spos[wstart_l[wl]], s1 = spos[wstart_l[wl + 1]];
+            const int4 ca = wc[a];
+            for (int sb = s0; sb < s1; sb += kWarp) {
+                const int s = sb + lane;
+                int b = 0;
+                bool keep = false;
+                if (s < s1) {
+                    b = samp[s];
+                    keep = wc_differs(ca, wc[b]);
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                if (keep) emit(out + __popc(bal & ((1u << lane) - 1u)), b);
+                out += __popc(bal);
+            }
+        }
+    }
+}
+
+// stand-alone rel-pos index for an existing CSR pair list (drop-in for stratified_transformer.py:186-188)
+__global__ void rel_index_csr_kernel(int N, const float *__restrict__ xyz, const int *__restrict__ offsets,
+                                     const int *__restrict__ index_1, float two_w, float quant, int *__restrict__ rel_idx) {
+    const int lane = threadIdx.x % kWarp;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp, nw = gridDim.x * blockDim.x / kWarp;
+    for (int a = wid; a < N; a += nw) {
+        const float xa = __ldg(xyz + (size_t)a * 3), ya = __ldg(xyz + (size_t)a * 3 + 1), za = __ldg(xyz + (size_t)a * 3 + 2);
+        const int s = offsets[a], e = offsets[a + 1];
+        for (int m = s + lane; m < e; m += kWarp) {
+            const int b = __ldg(index_1 + m);
+            rel_idx[(size_t)m * 3 + 0] = rel_index_stratified(xa, __ldg(xyz + (size_t)b * 3), two_w, quant);
+            rel_idx[(size_t)m * 3 + 1] = rel_index_stratified(ya, __ldg(xyz + (size_t)b * 3 + 1), two_w, quant);
+            rel_idx[(size_t)m * 3 + 2] = rel_index_stratified(za, __ldg(xyz + (size_t)b * 3 + 2), two_w, quant);
+        }
+    }
+}
+
+// Swin variant (swin3d_transformer.py:151-154,129-130): per-point quantised coordinate, then a difference
+__global__ void swin_quant_kernel(int N, const float *__restrict__ xyz, const unsigned *__restrict__ mm, float shift,
+                                  float w, float quant, float *__restrict__ xq) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N * 3; i += gridDim.x * blockDim.x) {
+        const float mn = ord2f(mm[i % 3]);
+        const float t = __fadd_rn(__fsub_rn(__ldg(xyz + i), mn), shift);
+        xq[i] = floor_div_f32(remainder_f32(t, w), quant);
+    }
+}
+__global__ void swin_rel_kernel(int N, const float *__restrict__ xq, const int *__restrict__ offsets,
+                                const int *__restrict__ index_1, float bias, int *__restrict__ rel_idx) {
+    const int lane = threadIdx.x % kWarp;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp, nw = gridDim.x * blockDim.x / kWarp;
+    for (int a = wid; a < N; a += nw) {
+        const int s = offsets[a], e = offsets[a + 1];
+        for (int m = s + lane; m < e; m += kWarp) {
+            const int b = __ldg(index_1 + m);
+#pragma unroll
+            for (int ax = 0; ax < 3; ++ax)
+                rel_idx[(size_t)m * 3 + ax] = (int)__fadd_rn(__fsub_rn(xq[(size_t)a * 3 + ax], xq[(size_t)b * 3 + ax]), bias);
+        }
+    }
+}
+
+static int blocks_for(long long n, int per_block = 256, int cap = kNumSMs * 8) {
+    return (int)max(1LL, min((n + per_block - 1) / per_block, (long long)cap));
+}
+
+}  // namespace stb200
+
+using namespace stb200;
+
+extern "C" {
+
+size_t stb200_pair_builder_workspace_bytes(int N) {
+    BuilderState st;
+    return carve(st, nullptr, N < 1 ? 1 : N);
+}
+
+int stb200_stratified_pairs_count(int N, int b, const float *xyz, const int *offset, float window_size, int parity,
+                                  const int *downsample_idx, int m, void *workspace, size_t workspace_bytes,
+                                  int *index0_offsets, int *totals, void *stream) {
+    STB200_REQUIRE(N > 0 && b > 0 && m >= 0, STB200_ERR_ARG, "bad sizes N=%d b=%d m=%d", N, b, m);
+    STB200_REQUIRE(xyz && offset && workspace && index0_offsets && totals && (m == 0 || downsample_idx), STB200_ERR_ARG,
+                   "null pointer");
+    STB200_REQUIRE(workspace_bytes >= stb200_pair_builder_workspace_bytes(N), STB200_ERR_WORKSPACE,
+                   "workspace too small: %zu < %zu", workspace_bytes, stb200_pair_builder_workspace_bytes(N));
+    cudaStream_t s = (cudaStream_t)stream;
+    BuilderState st;
+    carve(st, (char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255), N);
+    const int has_sparse = m > 0;
+    const int gb = blocks_for(N);
+    init_state_kernel<<<gb, 256, 0, s>>>(st.mm, st.gp, st.ds_mask, N);
+    minmax_kernel<<<blocks_for(N, 256, kNumSMs * 2), 256, 0, s>>>(N, xyz, st.mm);
+    if (has_sparse) mark_sampled_kernel<<<blocks_for(m), 256, 0, s>>>(m, downsample_idx, st.ds_mask, N);
+    params_kernel<<<1, 32, 0, s>>>(st.mm, st.gp, window_size, parity & 1, b);
+    keys_kernel<<<gb, 256, 0, s>>>(N, b, xyz, offset, st.gp, parity & 1, st.key_s, st.key_l, st.iota, st.wc);
+    size_t tb = st.cub_bytes;
+    cub::DeviceRadixSort::SortPairs(st.cub_tmp, tb, st.key_s, st.skey_s, st.iota, st.order_s, N, 0, 32, s);
+    tb = st.cub_bytes;
+    cub::DeviceRadixSort::SortPairs(st.cub_tmp, tb, st.key_l, st.skey_l, st.iota, st.order_l, N, 0, 32, s);
+    flags_kernel<<<gb, 256, 0, s>>>(N, st.skey_s, st.skey_l, st.order_l, st.ds_mask, st.flag_s, st.flag_l, st.sflag);
+    tb = st.cub_bytes;
+    cub::DeviceScan::InclusiveSum(st.cub_tmp, tb, st.flag_s, st.rank_s, N + 1, s);
+    tb = st.cub_bytes;
+    cub::DeviceScan::InclusiveSum(st.cub_tmp, tb, st.flag_l, st.rank_l, N + 1, s);
+    tb = st.cub_bytes;
+    cub::DeviceScan::ExclusiveSum(st.cub_tmp, tb, st.sflag, st.spos, N + 1, s);
+    scatter_windows_kernel<<<gb, 256, 0, s>>>(N, st.order_s, st.order_l, st.flag_s, st.flag_l, st.rank_s, st.rank_l,
+                                              st.sflag, st.spos, st.wstart_s, st.wstart_l, st.win_s, st.win_l, st.samp);
+    count_pairs_kernel<<<blocks_for((long long)N * kWarp), 256, 0, s>>>(N, st.win_s, st.win_l, st.wstart_s, st.wstart_l,
+                                                                       st.spos, st.samp, st.wc, st.counts, st.gp,
+                                                                       has_sparse);
+    tb = st.cub_bytes;
+    cub::DeviceScan::ExclusiveSum(st.cub_tmp, tb, st.counts, index0_offsets, N + 1, s);
+    finish_count_kernel<<<1, 32, 0, s>>>(N, index0_offsets, st.gp, totals);
+    count_launch(20);
+    return check_launch("stratified_pairs_count");
+}
+
+int stb200_stratified_pairs_fill(int N, const float *xyz, float window_size_x2, float quant_size, int has_sparse,
+                                 void *workspace, size_t workspace_bytes, const int *index0_offsets, int *index_1,
+                                 int *rel_idx, int *index_0, void *stream) {
+    STB200_REQUIRE(N > 0 && xyz && workspace && index0_offsets && index_1, STB200_ERR_ARG, "null pointer / bad N");
+    STB200_REQUIRE(workspace_bytes >= stb200_pair_builder_workspace_bytes(N), STB200_ERR_WORKSPACE, "workspace too small");
+    BuilderState st;
+    carve(st, (char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255), N);
+    fill_pairs_kernel<<<blocks_for((long long)N * kWarp), 256, 0, (cudaStream_t)stream>>>(
+        N, xyz, index0_offsets, st.win_s, st.win_l, st.wstart_s, st.wstart_l, st.order_s, st.spos, st.samp, st.wc,
+        has_sparse, window_size_x2, quant_size, index_1, rel_idx, index_0);
+    count_launch();
+    return check_launch("stratified_pairs_fill");
+}
+
+int stb200_rel_pos_index_stratified(int N, const float *xyz, const int *index0_offsets, const int *index_1,
+                                    float window_size_x2, float quant_size, int *rel_idx, void *stream) {
+    STB200_REQUIRE(N >= 0, STB200_ERR_ARG, "bad N");
+    if (N == 0) return STB200_OK;
+    STB200_REQUIRE(xyz && index0_offsets && index_1 && rel_idx, STB200_ERR_ARG, "null pointer");
+    rel_index_csr_kernel<<<blocks_for((long long)N * kWarp), 256, 0, (cudaStream_t)stream>>>(
+        N, xyz, index0_offsets, index_1, window_size_x2, quant_size, rel_idx);
+    count_launch();
+    return check_launch("rel_pos_index_stratified");
+}
+
+int stb200_rel_pos_index_swin(int N, const float *xyz, const int *index0_offsets, const int *index_1,
+                              float window_size, float quant_size, float shift_size, int quant_grid_length,
+                              float *xq_scratch /*[N,3]*/, unsigned *mm_scratch /*[6]*/, int *rel_idx, void *stream) {
+    STB200_REQUIRE(N >= 0, STB200_ERR_ARG, "bad N");
+    if (N == 0) return STB200_OK;
+    STB200_REQUIRE(xyz && index0_offsets && index_1 && rel_idx && xq_scratch && mm_scratch, STB200_ERR_ARG, "null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaMemsetAsync(mm_scratch, 0xff, 3 * sizeof(unsigned), s);
+    cudaMemsetAsync(mm_scratch + 3, 0, 3 * sizeof(unsigned), s);
+    minmax_kernel<<<blocks_for(N, 256, kNumSMs * 2), 256, 0, s>>>(N, xyz, mm_scratch);
+    swin_quant_kernel<<<blocks_for((long long)N * 3), 256, 0, s>>>(N, xyz, mm_scratch, shift_size, window_size, quant_size, xq_scratch);
+    swin_rel_kernel<<<blocks_for((long long)N * kWarp), 256, 0, s>>>(N, xq_scratch, index0_offsets, index_1,
+                                                                    (float)(quant_grid_length - 1), rel_idx);
+    count_launch(3);
+    return check_launch("rel_pos_index_swin");
+}
+
+}  // extern "C"

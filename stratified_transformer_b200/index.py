@@ -1,0 +1,135 @@
+"""Pair-index construction on the device (host-side mirror of the reference's Python).
+
+Replaces, for the attention hot path, `grid_sample` + `get_indice_pairs` + the sort/bincount/cumsum of
+`BasicLayer.forward` (/root/reference/model/stratified_transformer.py:10-65, 267-317) and the relative
+position index of `WindowAttention.forward` (:186-188; Swin: model/swin3d_transformer.py:151-154).
+
+The reference rebuilds the pair list for every block although only two distinct lists exist per layer
+(even blocks: unshifted windows, odd blocks: shifted).  `LayerIndex` builds both once per layer.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import torch
+
+from . import _cabi
+from . import pointops
+from . import pointops2_cuda as ext
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+@dataclass
+class PairIndex:
+    """CSR pair list of one block parity.  All index tensors are int32 on the device."""
+    index_0_offsets: torch.Tensor          # [N+1]
+    index_1: torch.Tensor                  # [M]   keys; per query: dense ascending id, then sparse ascending id
+    rel_idx: torch.Tensor | None           # [M,3] relative-position index
+    n_max: int
+    M: int
+    index_0: torch.Tensor | None = None    # [M]   only when asked for (v1 ops, scatter_softmax callers)
+    _tcsr: ext.TransposedCSR | None = field(default=None, repr=False)
+
+    @property
+    def N(self) -> int:
+        return self.index_0_offsets.numel() - 1
+
+    @property
+    def tcsr(self) -> ext.TransposedCSR:
+        """pairs grouped by key; built on first use (backward only)"""
+        if self._tcsr is None:
+            self._tcsr = ext.build_transposed_csr(self.index_0_offsets, self.index_1)
+        return self._tcsr
+
+
+def fps_new_offset(offset: torch.Tensor, downsample_scale: int) -> torch.Tensor:
+    """per scene n_i // ds + 1, cumulative (stratified_transformer.py:282-288), without the .item() loop."""
+    counts = torch.diff(offset, prepend=offset.new_zeros(1))
+    return torch.cumsum(torch.div(counts, downsample_scale, rounding_mode="floor") + 1, 0).to(torch.int32)
+
+
+def build_stratified_index(xyz: torch.Tensor, offset: torch.Tensor, window_size: float, quant_size: float | None,
+                           downsample_idx: torch.Tensor | None, parity: int, want_index_0: bool = False,
+                           workspace: torch.Tensor | None = None) -> PairIndex:
+    """One block parity of `get_indice_pairs` + sort + CSR (+ rel-pos index when quant_size is given).
+    downsample_idx=None gives dense window pairs only (the Swin / 3DSwin variant)."""
+    if not (xyz.is_cuda and xyz.dtype == torch.float32 and xyz.is_contiguous() and xyz.dim() == 2 and xyz.shape[1] == 3):
+        raise TypeError("xyz must be a contiguous CUDA float32 [N,3] tensor")
+    N, b = xyz.shape[0], offset.numel()
+    dev = xyz.device
+    offset = offset.to(device=dev, dtype=torch.int32).contiguous()
+    lib = _cabi.load()
+    nbytes = lib.stb200_pair_builder_workspace_bytes(N)
+    if workspace is None or workspace.numel() < nbytes:
+        workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    m = 0 if downsample_idx is None else downsample_idx.numel()
+    ds_ptr = None
+    if m:
+        downsample_idx = downsample_idx.to(torch.int32).contiguous()
+        ds_ptr = downsample_idx.data_ptr()
+    offsets = torch.empty(N + 1, dtype=torch.int32, device=dev)
+    totals = torch.empty(4, dtype=torch.int32, device=dev)
+    _cabi.call("stb200_stratified_pairs_count", N, b, xyz.data_ptr(), offset.data_ptr(), float(window_size),
+               int(parity) & 1, ds_ptr, m, workspace.data_ptr(), workspace.numel(), offsets.data_ptr(),
+               totals.data_ptr(), _stream())
+    M, n_max, err, _ = totals.tolist()      # the one host sync: the caller has to allocate M-sized outputs
+    if err:
+        raise _cabi.Stb200Error("pair builder: window grid has more than 2^32 cells (window too small for the scene extent)")
+    index_1 = torch.empty(M, dtype=torch.int32, device=dev)
+    rel_idx = torch.empty(M, 3, dtype=torch.int32, device=dev) if quant_size is not None else None
+    index_0 = torch.empty(M, dtype=torch.int32, device=dev) if want_index_0 else None
+    if M:
+        _cabi.call("stb200_stratified_pairs_fill", N, xyz.data_ptr(), float(2 * window_size),
+                   float(quant_size if quant_size is not None else 1.0), int(m > 0), workspace.data_ptr(),
+                   workspace.numel(), offsets.data_ptr(), index_1.data_ptr(),
+                   None if rel_idx is None else rel_idx.data_ptr(), None if index_0 is None else index_0.data_ptr(),
+                   _stream())
+    return PairIndex(offsets, index_1, rel_idx, int(n_max), int(M), index_0)
+
+
+def rel_pos_index_stratified(xyz, index_0_offsets, index_1, window_size: float, quant_size: float) -> torch.Tensor:
+    """relative_position_index of stratified_transformer.py:186-188 for an existing CSR pair list -> int32 [M,3]."""
+    N = index_0_offsets.numel() - 1
+    out = torch.empty(index_1.numel(), 3, dtype=torch.int32, device=xyz.device)
+    _cabi.call("stb200_rel_pos_index_stratified", N, xyz.data_ptr(), index_0_offsets.data_ptr(), index_1.data_ptr(),
+               float(2 * window_size), float(quant_size), out.data_ptr(), _stream())
+    return out
+
+
+def rel_pos_index_swin(xyz, index_0_offsets, index_1, window_size: float, quant_size: float, shift_size: float) -> torch.Tensor:
+    """relative_position_index of swin3d_transformer.py:151-154 (+ map_func :129-130) -> int32 [M,3]."""
+    N = index_0_offsets.numel() - 1
+    out = torch.empty(index_1.numel(), 3, dtype=torch.int32, device=xyz.device)
+    xq = torch.empty(N, 3, dtype=torch.float32, device=xyz.device)
+    mm = torch.empty(6, dtype=torch.int32, device=xyz.device)
+    _cabi.call("stb200_rel_pos_index_swin", N, xyz.data_ptr(), index_0_offsets.data_ptr(), index_1.data_ptr(),
+               float(window_size), float(quant_size), float(shift_size), int(window_size / quant_size),
+               xq.data_ptr(), mm.data_ptr(), out.data_ptr(), _stream())
+    return out
+
+
+@dataclass
+class LayerIndex:
+    """Everything `BasicLayer.forward` derives from (xyz, offset) before its block loop:
+    FPS-sampled key candidates and the two pair lists (even / odd blocks)."""
+    downsample_idx: torch.Tensor | None
+    parity: tuple
+
+    def for_block(self, i: int) -> PairIndex:
+        return self.parity[i % 2]
+
+
+def build_layer_index(xyz: torch.Tensor, offset: torch.Tensor, window_size: float, quant_size: float,
+                      downsample_scale: int | None, want_index_0: bool = False, parities=(0, 1)) -> LayerIndex:
+    """stratified_transformer.py:267-317 for one layer: FPS (n_i // ds + 1 samples per scene), then both parities.
+    downsample_scale=None -> dense-only pairs (Swin)."""
+    offset = offset.to(device=xyz.device, dtype=torch.int32)
+    ds_idx = None
+    if downsample_scale is not None:
+        ds_idx = pointops.furthestsampling(xyz, offset, fps_new_offset(offset, downsample_scale))
+    ws = torch.empty(_cabi.load().stb200_pair_builder_workspace_bytes(xyz.shape[0]), dtype=torch.uint8, device=xyz.device)
+    built = {p: build_stratified_index(xyz, offset, window_size, quant_size, ds_idx, p, want_index_0, ws) for p in parities}
+    return LayerIndex(ds_idx, tuple(built.get(p) for p in (0, 1)))

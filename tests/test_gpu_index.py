@@ -1,0 +1,139 @@
+"""Pair-index construction on the GPU (-m gpu): bit-exact against the reference-generated golden
+fixtures (tests/golden/index_*.npz) and against the CPU oracle at larger sizes."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fps_oracle, index_oracle as io
+
+pytestmark = pytest.mark.gpu
+CASES = ["s3dis_small", "s3dis_lattice", "scannet_small"]
+
+
+def build(xyz, offset, w, quant, ds_idx, parity, want_index_0=False):
+    from stratified_transformer_b200 import index
+    return index.build_stratified_index(torch.from_numpy(xyz).cuda(), torch.from_numpy(offset).cuda(), w, quant,
+                                        None if ds_idx is None else torch.from_numpy(ds_idx).cuda(), parity,
+                                        want_index_0=want_index_0)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_pairs_match_reference_golden(golden_dir, name):
+    from stratified_transformer_b200 import index, pointops
+    g = np.load(os.path.join(golden_dir, f"index_{name}.npz"))
+    xyz, offset = g["xyz"], g["offset"]
+    w, quant, ds = float(g["window_size"]), float(g["quant_size"]), int(g["downsample_scale"])
+    off_d = torch.from_numpy(offset).cuda()
+    new_offset = index.fps_new_offset(off_d, ds)
+    assert np.array_equal(new_offset.cpu().numpy(), g["new_offset"])
+    ds_idx = pointops.furthestsampling(torch.from_numpy(xyz).cuda(), off_d, new_offset).cpu().numpy()
+    assert np.array_equal(ds_idx, g["downsample_idx"])
+    for parity in (0, 1):
+        r = build(xyz, offset, w, quant, ds_idx, parity, want_index_0=True)
+        offs = r.index_0_offsets.cpu().numpy()
+        assert np.array_equal(offs, g[f"p{parity}_offsets"])
+        assert r.n_max == int(g[f"p{parity}_n_max"]) and r.M == offs[-1]
+        i1 = r.index_1.cpu().numpy()
+        # multiset per query == the reference's (canonicalised because its sorts are unstable)
+        assert np.array_equal(io.canonicalize(offs, i1), g[f"p{parity}_index_1"])
+        # exact emitted order == the oracle's canonical order (dense ascending, then sparse ascending)
+        o = io.build_layer_index(xyz, offset, w, ds, ds_idx, parity)
+        assert np.array_equal(i1, o["index_1"])
+        assert np.array_equal(r.index_0.cpu().numpy(), o["index_0"])
+        rel = r.rel_idx.cpu().numpy()
+        assert np.array_equal(rel, io.rel_pos_index_stratified(xyz, o["index_0"], o["index_1"], w, quant))
+        # and the rel-pos index agrees with the reference's torch evaluation once both are canonicalised
+        seg = np.repeat(np.arange(offs.shape[0] - 1), np.diff(offs))
+        order = np.lexsort((i1, seg))
+        want = g[f"p{parity}_rel_idx"].astype(np.int32)
+        same_key_runs = np.array_equal(np.sort(rel[order], axis=0), np.sort(want, axis=0))
+        assert same_key_runs
+
+
+def test_pairs_vs_oracle_two_scenes_20k():
+    from stratified_transformer_b200.synthetic import make_batch
+    xyz, _, offset = make_batch(2, 20000, seed0=3, n_raw=600_000)
+    w, quant, ds = 0.32, 0.02, 8      # S3DIS layer-1 geometry
+    new_offset = io.fps_new_offset(offset, ds)
+    ds_idx = fps_oracle.furthestsampling(xyz, offset, new_offset)
+    for parity in (0, 1):
+        r = build(xyz, offset, w, quant, ds_idx, parity)
+        o = io.build_layer_index(xyz, offset, w, ds, ds_idx, parity)
+        assert np.array_equal(r.index_0_offsets.cpu().numpy(), o["offsets"])
+        assert np.array_equal(r.index_1.cpu().numpy(), o["index_1"])
+        assert r.n_max == o["n_max"]
+        assert np.array_equal(r.rel_idx.cpu().numpy(), io.rel_pos_index_stratified(xyz, o["index_0"], o["index_1"], w, quant))
+
+
+def test_dense_only_pairs_swin_invariant(golden_dir):
+    """Swin builds dense window pairs only; the reference asserts M == (counts**2).sum()
+    (model/swin3d_transformer.py:258-259)."""
+    g = np.load(os.path.join(golden_dir, "index_s3dis_small.npz"))
+    xyz, offset = g["xyz"], g["offset"]
+    for parity in (0, 1):
+        r = build(xyz, offset, 0.16, None, None, parity)
+        batch = io.batch_from_offset(offset)
+        w = np.full(3, 0.16, np.float32)
+        if parity == 0:
+            _, _, counts = io.grid_sample(xyz, batch, w, None)
+        else:
+            _, _, counts = io.grid_sample((xyz + np.float32(0.5) * w).astype(np.float32), batch, w, xyz.min(0))
+        assert r.M == int((counts ** 2).sum())
+        assert r.rel_idx is None
+
+
+def test_rel_pos_index_standalone_and_swin(golden_dir):
+    from stratified_transformer_b200 import index
+    g = np.load(os.path.join(golden_dir, "relidx_swin.npz"))
+    xyz, i0, i1 = g["xyz"], g["index_0"].astype(np.int64), g["index_1"].astype(np.int64)
+    N = xyz.shape[0]
+    offsets = np.concatenate([[0], np.cumsum(np.bincount(i0, minlength=N))]).astype(np.int32)
+    xd, od, i1d = torch.from_numpy(xyz).cuda(), torch.from_numpy(offsets).cuda(), torch.from_numpy(i1).cuda().int()
+    for shift, tag in ((0.0, "noshift"), (0.08, "shift")):
+        got = index.rel_pos_index_swin(xd, od, i1d, 0.16, 0.01, shift).cpu().numpy()
+        assert np.array_equal(got, g[f"rel_idx_{tag}"].astype(np.int32))
+    got = index.rel_pos_index_stratified(xd, od, i1d, 4.0, 0.25).cpu().numpy()   # any geometry: arithmetic check only
+    assert np.array_equal(got, io.rel_pos_index_stratified(xyz, i0, i1, 4.0, 0.25))
+
+
+def test_window_attention_module_vs_oracle(golden_dir):
+    """The WindowAttention mirror (reference call signature AND PairIndex form) against a CPU
+    composition of the oracle ops around the same Linear layers."""
+    from oracle import attention_oracle as ao
+    from stratified_transformer_b200 import index
+    from stratified_transformer_b200.window_attention import WindowAttention
+    g = np.load(os.path.join(golden_dir, "index_s3dis_small.npz"))
+    xyz, offset = g["xyz"], g["offset"]
+    ds_idx = g["downsample_idx"]
+    torch.manual_seed(0)
+    C, h = 48, 3
+    mod = WindowAttention(C, 0.16, h, 0.01, rel_query=True, rel_key=True, rel_value=True).cuda()
+    feats = torch.randn(xyz.shape[0], C)
+    pi = build(xyz, offset, 0.16, 0.01, ds_idx, 1, want_index_0=True)
+    xd = torch.from_numpy(xyz).cuda()
+    fd = feats.cuda().requires_grad_(True)
+    out = mod(fd, xd, pi)
+    # reference-style call with int64 tensors gives the same result
+    out2 = mod(fd, xd, pi.index_0.long(), pi.index_1.long(), pi.index_0_offsets.long(), torch.tensor(pi.n_max).cuda())
+    assert torch.allclose(out, out2, atol=1e-6)
+    gout = torch.randn_like(out)
+    out.backward(gout)
+    # CPU: same Linear weights, oracle ops in fp64 with autograd through layer_autograd's formulation
+    W = {k: v.detach().double().cpu() for k, v in mod.state_dict().items()}
+    f = feats.double().requires_grad_(True)
+    qkv = (f @ W["qkv.weight"].T + W["qkv.bias"]).reshape(-1, 3, h, C // h).permute(1, 0, 2, 3)
+    q, k, v = qkv[0] * mod.scale, qkv[1], qkv[2]
+    i0 = pi.index_0.long().cpu(); i1 = pi.index_1.long().cpu(); r = pi.rel_idx.long().cpu()
+    tq, tk, tv = (W[f"relative_pos_{n}_table"] for n in ("query", "key", "value"))
+    eq = ao.table_sum(tq, r); ek = ao.table_sum(tk, r); ev = ao.table_sum(tv, r)
+    s = (q[i0] * k[i1]).sum(-1) + (q[i0] * eq + k[i1] * ek).sum(-1)
+    p = ao.softmax_fwd(s.detach(), i0, f.shape[0])
+    ex = torch.exp(s - s.detach().new_full((f.shape[0], h), -1e30).scatter_reduce(0, i0[:, None].expand(-1, h), s.detach(), "amax")[i0])
+    p = ex / torch.zeros(f.shape[0], h, dtype=torch.float64).index_add(0, i0, ex)[i0]
+    x = torch.zeros(f.shape[0], h, C // h, dtype=torch.float64).index_add(0, i0, p.unsqueeze(-1) * (v[i1] + ev))
+    ref = x.reshape(-1, C) @ W["proj.weight"].T + W["proj.bias"]
+    ref.backward(gout.double().cpu())
+    assert torch.allclose(out.detach().double().cpu(), ref.detach(), rtol=2e-4, atol=2e-5)
+    assert torch.allclose(fd.grad.double().cpu(), f.grad, rtol=2e-3, atol=2e-5)

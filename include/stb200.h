@@ -44,6 +44,11 @@ const char *stb200_last_error(void);
 /* number of kernels this library launched since load (bench.py's "gpu_launches") */
 long long stb200_launch_count(void);
 int stb200_version(void);
+/* Optional per-kernel profiler: when enabled every launch is bracketed by CUDA events on its stream.
+ * stb200_profile_dump writes a JSON object {"kernel name": {"launches", "ms", "bytes"}} (bytes = algorithmic bytes
+ * of those launches, DESIGN.md "Roofline accounting") into buf, clears the records, returns the size needed. */
+void stb200_profile_enable(int on);
+size_t stb200_profile_dump(char *buf, size_t cap);
 
 /* ------------------------------------------------------------------------------------------------
  * Transposed CSR: pairs grouped by key.  For key j, t in [t_offsets[j], t_offsets[j+1]) enumerates its
@@ -165,7 +170,7 @@ int stb200_stratified_pairs_count(int N, int b, const float *xyz, const int *off
                                   int *index0_offsets, int *totals, void *stream);
 int stb200_stratified_pairs_fill(int N, const float *xyz, float window_size_x2, float quant_size, int has_sparse,
                                  void *workspace, size_t workspace_bytes, const int *index0_offsets, int *index_1,
-                                 int *rel_idx, int *index_0, void *stream);
+                                 int *rel_idx, int *index_0, int M, void *stream);
 
 /* Relative-position index of an existing CSR pair list.
  * Stratified: idx = ((round((xyz[i0]-xyz[i1])*1e5)/1e5) + 2w - 1e-4) // quant  (stratified_transformer.py:186-188)

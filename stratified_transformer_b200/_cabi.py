@@ -35,7 +35,7 @@ _SIGNATURES = {
     "stb200_attention_step2_with_rel_pos_value_backward": [_c_int] * 5 + [P] * 11,
     "stb200_furthestsampling": [_c_int, _c_int] + [P] * 6,
     "stb200_stratified_pairs_count": [_c_int, _c_int, P, P, ctypes.c_float, _c_int, P, _c_int, P, _c_size_t, P, P, P],
-    "stb200_stratified_pairs_fill": [_c_int, P, ctypes.c_float, ctypes.c_float, _c_int, P, _c_size_t, P, P, P, P, P],
+    "stb200_stratified_pairs_fill": [_c_int, P, ctypes.c_float, ctypes.c_float, _c_int, P, _c_size_t, P, P, P, P, _c_int, P],
     "stb200_rel_pos_index_stratified": [_c_int, P, P, P, ctypes.c_float, ctypes.c_float, P, P],
     "stb200_rel_pos_index_swin": [_c_int, P, P, P, ctypes.c_float, ctypes.c_float, ctypes.c_float, _c_int, P, P, P, P],
 }
@@ -45,6 +45,8 @@ _RESTYPES = {
     "stb200_version": (_c_int, []),
     "stb200_transpose_csr_workspace_bytes": (_c_size_t, [_c_int, _c_int]),
     "stb200_pair_builder_workspace_bytes": (_c_size_t, [_c_int]),
+    "stb200_profile_enable": (None, [_c_int]),
+    "stb200_profile_dump": (_c_size_t, [ctypes.c_char_p, _c_size_t]),
 }
 
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + list(_RESTYPES))
@@ -89,3 +91,17 @@ def call(name: str, *args):
 
 def launch_count() -> int:
     return int(load().stb200_launch_count())
+
+
+def profile_enable(on: bool = True) -> None:
+    load().stb200_profile_enable(1 if on else 0)
+
+
+def profile_dump() -> dict:
+    """Per-kernel totals since the last dump: {name: {"launches", "ms", "bytes"}} (synchronises)."""
+    import json
+    lib = load()
+    n = lib.stb200_profile_dump(None, 0)
+    buf = ctypes.create_string_buffer(n + 16)
+    lib.stb200_profile_dump(buf, n + 16)
+    return json.loads(buf.value.decode())

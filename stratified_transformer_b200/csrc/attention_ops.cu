@@ -399,64 +399,83 @@ static int pick_hg(int h, int D, int L, int ntables) {
     return largest_head_group(h, cap);
 }
 
+// algorithmic bytes of one launch: every input read once, every output written once
+static double seg_bytes(const SegParams &p, int D, int M, bool rows_x, bool rows_y, bool weights, bool gather, bool perm,
+                        int ntables, bool out_pairs) {
+    const double C = (double)p.h * D, N = p.N;
+    double b = 4.0 * (N + 1);                                // offsets
+    if (rows_x) b += 4.0 * N * C;
+    if (rows_y) b += 4.0 * N * C;
+    if (weights) b += 4.0 * M * p.h;
+    if (gather) b += 4.0 * M;
+    if (perm) b += 4.0 * M;
+    if (ntables) b += 12.0 * M + ntables * 12.0 * p.L * C;   // rel_idx + tables
+    b += out_pairs ? 4.0 * M * p.h : 4.0 * N * C * (p.accumulate ? 2 : 1);
+    return b;
+}
+
 template <int D, int HG, bool XY, bool EX, bool EY>
-static int launch_seg_dot_hg(const SegParams &p, cudaStream_t s) {
+static int launch_seg_dot_hg(const SegParams &p, int M, const char *name, cudaStream_t s) {
     const size_t smem = ((size_t)(EX + EY) * 3 * p.L * HG * D + (kThreads / kWarp) * HG * D) * sizeof(float);
     auto kern = seg_dot_kernel<D, HG, XY, EX, EY>;
     if (int rc = prep_smem(kern, smem)) return rc;
     dim3 grid(grid_rows(p.N, smem, p.h / HG), p.h / HG);
-    kern<<<grid, kThreads, smem, s>>>(p);
-    count_launch();
-    return check_launch("seg_dot");
+    {
+        KernelScope ks(name, seg_bytes(p, D, M, true, true, false, true, false, EX + EY, true), s);
+        kern<<<grid, kThreads, smem, s>>>(p);
+    }
+    return check_launch(name);
 }
 
 template <int D, bool XY, bool EX, bool EY>
-static int launch_seg_dot_d(const SegParams &p, cudaStream_t s) {
+static int launch_seg_dot_d(const SegParams &p, int M, const char *name, cudaStream_t s) {
     switch (pick_hg(p.h, D, p.L, EX + EY)) {
-        case 4: return launch_seg_dot_hg<D, 4, XY, EX, EY>(p, s);
-        case 3: return launch_seg_dot_hg<D, 3, XY, EX, EY>(p, s);
-        case 2: return launch_seg_dot_hg<D, 2, XY, EX, EY>(p, s);
-        default: return launch_seg_dot_hg<D, 1, XY, EX, EY>(p, s);
+        case 4: return launch_seg_dot_hg<D, 4, XY, EX, EY>(p, M, name, s);
+        case 3: return launch_seg_dot_hg<D, 3, XY, EX, EY>(p, M, name, s);
+        case 2: return launch_seg_dot_hg<D, 2, XY, EX, EY>(p, M, name, s);
+        default: return launch_seg_dot_hg<D, 1, XY, EX, EY>(p, M, name, s);
     }
 }
 
 template <bool XY, bool EX, bool EY>
-static int launch_seg_dot(int D, const SegParams &p, cudaStream_t s) {
+static int launch_seg_dot(int D, const SegParams &p, int M, const char *name, cudaStream_t s) {
     if (p.N == 0) return STB200_OK;
-    if (D == 16) return launch_seg_dot_d<16, XY, EX, EY>(p, s);
-    return launch_seg_dot_d<32, XY, EX, EY>(p, s);
+    if (D == 16) return launch_seg_dot_d<16, XY, EX, EY>(p, M, name, s);
+    return launch_seg_dot_d<32, XY, EX, EY>(p, M, name, s);
 }
 
 template <int D, int HG, bool HAS_Y, bool HAS_T, bool PERM>
-static int launch_seg_reduce_hg(const SegParams &p, cudaStream_t s) {
+static int launch_seg_reduce_hg(const SegParams &p, int M, const char *name, cudaStream_t s) {
     const size_t smem = (size_t)HAS_T * 3 * p.L * HG * D * sizeof(float);
     auto kern = seg_reduce_kernel<D, HG, HAS_Y, HAS_T, PERM>;
     if (int rc = prep_smem(kern, smem)) return rc;
     dim3 grid(grid_rows(p.N, smem, p.h / HG), p.h / HG);
-    kern<<<grid, kThreads, smem, s>>>(p);
-    count_launch();
-    return check_launch("seg_reduce");
+    {
+        KernelScope ks(name, seg_bytes(p, D, M, false, HAS_Y, true, HAS_Y, PERM, HAS_T, false), s);
+        kern<<<grid, kThreads, smem, s>>>(p);
+    }
+    return check_launch(name);
 }
 
 template <int D, bool HAS_Y, bool HAS_T, bool PERM>
-static int launch_seg_reduce_d(const SegParams &p, cudaStream_t s) {
+static int launch_seg_reduce_d(const SegParams &p, int M, const char *name, cudaStream_t s) {
     switch (pick_hg(p.h, D, p.L, HAS_T)) {
-        case 4: return launch_seg_reduce_hg<D, 4, HAS_Y, HAS_T, PERM>(p, s);
-        case 3: return launch_seg_reduce_hg<D, 3, HAS_Y, HAS_T, PERM>(p, s);
-        case 2: return launch_seg_reduce_hg<D, 2, HAS_Y, HAS_T, PERM>(p, s);
-        default: return launch_seg_reduce_hg<D, 1, HAS_Y, HAS_T, PERM>(p, s);
+        case 4: return launch_seg_reduce_hg<D, 4, HAS_Y, HAS_T, PERM>(p, M, name, s);
+        case 3: return launch_seg_reduce_hg<D, 3, HAS_Y, HAS_T, PERM>(p, M, name, s);
+        case 2: return launch_seg_reduce_hg<D, 2, HAS_Y, HAS_T, PERM>(p, M, name, s);
+        default: return launch_seg_reduce_hg<D, 1, HAS_Y, HAS_T, PERM>(p, M, name, s);
     }
 }
 
 template <bool HAS_Y, bool HAS_T, bool PERM>
-static int launch_seg_reduce(int D, const SegParams &p, cudaStream_t s) {
+static int launch_seg_reduce(int D, const SegParams &p, int M, const char *name, cudaStream_t s) {
     if (p.N == 0) return STB200_OK;
-    if (D == 16) return launch_seg_reduce_d<16, HAS_Y, HAS_T, PERM>(p, s);
-    return launch_seg_reduce_d<32, HAS_Y, HAS_T, PERM>(p, s);
+    if (D == 16) return launch_seg_reduce_d<16, HAS_Y, HAS_T, PERM>(p, M, name, s);
+    return launch_seg_reduce_d<32, HAS_Y, HAS_T, PERM>(p, M, name, s);
 }
 
 template <int D, bool PERM>
-static int launch_table_grad_d(const SegParams &p, cudaStream_t s) {
+static int launch_table_grad_d(const SegParams &p, int M, const char *name, cudaStream_t s) {
     constexpr int RPT = 4;
     constexpr int NL = kThreads / (D / 4);
     const int R = 3 * p.L;
@@ -467,17 +486,17 @@ static int launch_table_grad_d(const SegParams &p, cudaStream_t s) {
     const int ctas_per_sm = max(1, min(4, (int)((200 * 1024) / smem)));
     const int gx = max(1, min(tiles, (kNumSMs * ctas_per_sm + p.h - 1) / p.h));
     for (int pass = 0; pass < R; pass += NL * RPT) {
+        KernelScope ks(name, seg_bytes(p, D, M, true, false, true, false, PERM, 1, false) - 4.0 * p.N * p.h * D, s);
         kern<<<dim3(gx, p.h), kThreads, smem, s>>>(p, pass);
-        count_launch();
     }
-    return check_launch("table_grad");
+    return check_launch(name);
 }
 
 template <bool PERM>
-static int launch_table_grad(int D, const SegParams &p, cudaStream_t s) {
+static int launch_table_grad(int D, const SegParams &p, int M, const char *name, cudaStream_t s) {
     if (p.N == 0) return STB200_OK;
-    if (D == 16) return launch_table_grad_d<16, PERM>(p, s);
-    return launch_table_grad_d<32, PERM>(p, s);
+    if (D == 16) return launch_table_grad_d<16, PERM>(p, M, name, s);
+    return launch_table_grad_d<32, PERM>(p, M, name, s);
 }
 
 static int check_dims(int N, int M, int h, int D) {
@@ -500,7 +519,7 @@ int stb200_attention_step1_forward_v2(int N, int M, int h, int C, unsigned int, 
     STB200_REQUIRE(q && k && index0_offsets && index1 && attn, STB200_ERR_ARG, "null pointer");
     SegParams p{};
     p.N = N; p.h = h; p.L = 0; p.X = q; p.Y = k; p.offsets = index0_offsets; p.gather_idx = index1; p.out = attn;
-    return launch_seg_dot<true, false, false>(C / h, p, (cudaStream_t)stream);
+    return launch_seg_dot<true, false, false>(C / h, p, M, "seg_dot[step1_fwd]", (cudaStream_t)stream);
 }
 
 int stb200_attention_step1_backward_v2(int N, int M, int h, int C, unsigned int, const float *grad_out,
@@ -514,9 +533,9 @@ int stb200_attention_step1_backward_v2(int N, int M, int h, int C, unsigned int,
     cudaStream_t s = (cudaStream_t)stream;
     SegParams p{};
     p.N = N; p.h = h; p.w = grad_out; p.Y = k; p.offsets = index0_offsets; p.gather_idx = index1; p.out = grad_q;
-    if (int rc = launch_seg_reduce<true, false, false>(C / h, p, s)) return rc;   // grad_q: overwritten (ref :90)
+    if (int rc = launch_seg_reduce<true, false, false>(C / h, p, M, "seg_reduce[step1_bwd_gq]", s)) return rc;   // grad_q: overwritten (ref :90)
     p.Y = q; p.offsets = t_offsets; p.gather_idx = t_index0; p.pair_id = t_pair; p.out = grad_k; p.accumulate = 1;
-    return launch_seg_reduce<true, false, true>(C / h, p, s);                     // grad_k: accumulated (ref :84)
+    return launch_seg_reduce<true, false, true>(C / h, p, M, "seg_reduce_t[step1_bwd_gk]", s);  // grad_k: accumulated (ref :84)
 }
 
 int stb200_dot_prod_with_idx_forward_v3(int N, int M, int h, int hdim, int, int L, const float *q,
@@ -530,7 +549,7 @@ int stb200_dot_prod_with_idx_forward_v3(int N, int M, int h, int hdim, int, int 
     SegParams p{};
     p.N = N; p.h = h; p.L = L; p.X = q; p.Y = k; p.offsets = index_q_offsets; p.gather_idx = index_k;
     p.Tx = table_q; p.Ty = table_k; p.rel_idx = rel_idx; p.out = output;
-    return launch_seg_dot<false, true, true>(hdim, p, (cudaStream_t)stream);
+    return launch_seg_dot<false, true, true>(hdim, p, M, "seg_dot[rpe_fwd]", (cudaStream_t)stream);
 }
 
 int stb200_dot_prod_with_idx_backward_v3(int N, int M, int h, int hdim, int, int L, const float *grad_out,
@@ -547,14 +566,14 @@ int stb200_dot_prod_with_idx_backward_v3(int N, int M, int h, int hdim, int, int
     SegParams p{};
     p.N = N; p.h = h; p.L = L; p.w = grad_out; p.rel_idx = rel_idx;
     p.offsets = index_q_offsets; p.Tx = table_q; p.out = grad_q;
-    if (int rc = launch_seg_reduce<false, true, false>(hdim, p, s)) return rc;    // grad_q = sum g*Eq (overwritten, ref :338)
+    if (int rc = launch_seg_reduce<false, true, false>(hdim, p, M, "seg_reduce[rpe_bwd_gq]", s)) return rc;    // grad_q = sum g*Eq (overwritten, ref :338)
     p.X = q; p.out = grad_table_q;
-    if (int rc = launch_table_grad<false>(hdim, p, s)) return rc;                 // grad_table_q (+=)
+    if (int rc = launch_table_grad<false>(hdim, p, M, "table_grad[rpe_bwd_gtq]", s)) return rc;  // grad_table_q (+=)
     p.offsets = t_offsets; p.pair_id = t_pair; p.gather_idx = t_index0;
     p.Tx = table_k; p.out = grad_k; p.accumulate = 1;
-    if (int rc = launch_seg_reduce<false, true, true>(hdim, p, s)) return rc;     // grad_k += sum g*Ek
+    if (int rc = launch_seg_reduce<false, true, true>(hdim, p, M, "seg_reduce_t[rpe_bwd_gk]", s)) return rc;     // grad_k += sum g*Ek
     p.X = k; p.out = grad_table_k;
-    return launch_table_grad<true>(hdim, p, s);                                   // grad_table_k (+=)
+    return launch_table_grad<true>(hdim, p, M, "table_grad_t[rpe_bwd_gtk]", s);    // grad_table_k (+=)
 }
 
 int stb200_attention_step2_with_rel_pos_value_forward_v2(int N, int M, int h, int hdim, int, int L, const float *attn,
@@ -567,7 +586,7 @@ int stb200_attention_step2_with_rel_pos_value_forward_v2(int N, int M, int h, in
     SegParams p{};
     p.N = N; p.h = h; p.L = L; p.w = attn; p.Y = v; p.offsets = index0_offsets; p.gather_idx = index1;
     p.Tx = table; p.rel_idx = rel_idx; p.out = output;
-    return launch_seg_reduce<true, true, false>(hdim, p, (cudaStream_t)stream);
+    return launch_seg_reduce<true, true, false>(hdim, p, M, "seg_reduce[step2_fwd]", (cudaStream_t)stream);
 }
 
 int stb200_attention_step2_with_rel_pos_value_backward_v2(int N, int M, int h, int hdim, int, int L,
@@ -585,12 +604,12 @@ int stb200_attention_step2_with_rel_pos_value_backward_v2(int N, int M, int h, i
     p.N = N; p.h = h; p.L = L; p.rel_idx = rel_idx;
     p.X = grad_out; p.Y = v; p.offsets = index0_offsets; p.gather_idx = index1; p.Tx = table; p.out = grad_attn;
     if (M > 0)
-        if (int rc = launch_seg_dot<true, true, false>(hdim, p, s)) return rc;    // grad_attn = <g, v + Ev>
+        if (int rc = launch_seg_dot<true, true, false>(hdim, p, M, "seg_dot[step2_bwd_gattn]", s)) return rc;    // grad_attn = <g, v + Ev>
     p.w = attn; p.out = grad_table;
-    if (int rc = launch_table_grad<false>(hdim, p, s)) return rc;                 // grad_table (+=), X = grad_out
+    if (int rc = launch_table_grad<false>(hdim, p, M, "table_grad[step2_bwd_gtv]", s)) return rc;  // grad_table (+=), X = grad_out
     p.Y = grad_out; p.offsets = t_offsets; p.pair_id = t_pair; p.gather_idx = t_index0; p.out = grad_v;
     p.accumulate = 1;
-    return launch_seg_reduce<true, false, true>(hdim, p, s);                      // grad_v += sum attn*g
+    return launch_seg_reduce<true, false, true>(hdim, p, M, "seg_reduce_t[step2_bwd_gv]", s);  // grad_v += sum attn*g
 }
 
 int stb200_segment_softmax_forward(int N, int M, int h, const float *a, const float *b, const int *index0_offsets,
@@ -599,8 +618,10 @@ int stb200_segment_softmax_forward(int N, int M, int h, const float *a, const fl
     if (N == 0 || M == 0) return STB200_OK;
     STB200_REQUIRE(a && index0_offsets && p, STB200_ERR_ARG, "null pointer");
     const int blocks = max(1, min((N + kThreads / kWarp - 1) / (kThreads / kWarp), kNumSMs * 8));
-    segment_softmax_fwd_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(N, h, a, b, index0_offsets, p);
-    count_launch();
+    {
+        KernelScope ks("segment_softmax_fwd", 4.0 * M * h * (b ? 3 : 2) + 4.0 * (N + 1), (cudaStream_t)stream);
+        segment_softmax_fwd_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(N, h, a, b, index0_offsets, p);
+    }
     return check_launch("segment_softmax_fwd");
 }
 
@@ -610,8 +631,10 @@ int stb200_segment_softmax_backward(int N, int M, int h, const float *p, const f
     if (N == 0 || M == 0) return STB200_OK;
     STB200_REQUIRE(p && grad_p && index0_offsets && grad_s, STB200_ERR_ARG, "null pointer");
     const int blocks = max(1, min((N + kThreads / kWarp - 1) / (kThreads / kWarp), kNumSMs * 8));
-    segment_softmax_bwd_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(N, h, p, grad_p, index0_offsets, grad_s);
-    count_launch();
+    {
+        KernelScope ks("segment_softmax_bwd", 4.0 * M * h * 3 + 4.0 * (N + 1), (cudaStream_t)stream);
+        segment_softmax_bwd_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(N, h, p, grad_p, index0_offsets, grad_s);
+    }
     return check_launch("segment_softmax_bwd");
 }
 

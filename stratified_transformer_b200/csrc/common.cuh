@@ -14,6 +14,17 @@ void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
 int check_launch(const char *what);  // cudaGetLastError -> STB200_ERR_CUDA
 
+// Declared around every kernel launch: counts it and, when profiling is on, brackets it with CUDA events on the
+// launching stream.  algorithmic_bytes = what this launch must read + write once ("Roofline accounting").
+class KernelScope {
+  public:
+    KernelScope(const char *name, double algorithmic_bytes, cudaStream_t stream);
+    ~KernelScope();
+  private:
+    cudaStream_t stream_;
+    int idx_;
+};
+
 #define STB200_REQUIRE(cond, code, ...)        \
     do {                                       \
         if (!(cond)) {                         \

@@ -219,6 +219,7 @@ static int launch_fps(int b, int cs, const float *xyz, const int *offset, const 
                       cudaStream_t s) {
     const size_t smem = (size_t)3 * P * kFpsThreads * sizeof(float);
     cudaError_t e;
+    KernelScope ks("fps_cluster", 0.0, s);  // latency-bound by construction: bytes are not the meaningful unit
     if (cs == 1) {
         auto kern = fps_kernel<P, false>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) {
@@ -250,7 +251,6 @@ static int launch_fps(int b, int cs, const float *xyz, const int *offset, const 
             return STB200_ERR_CUDA;
         }
     }
-    count_launch();
     return check_launch("fps");
 }
 
@@ -278,7 +278,9 @@ extern "C" int stb200_furthestsampling(int b, int n, const float *xyz, const int
     if (need <= 6) return launch_fps<6>(b, cs, xyz, offset, new_offset, idx, logB, s);
     if (need <= 8) return launch_fps<8>(b, cs, xyz, offset, new_offset, idx, logB, s);
     STB200_REQUIRE(tmp, STB200_ERR_ARG, "scene of %d points needs the tmp scratch (streaming path)", n);
-    fps_streaming_kernel<<<b, kFpsThreads, 0, s>>>(xyz, offset, new_offset, tmp, idx, logB);
-    count_launch();
+    {
+        KernelScope ks("fps_streaming", 0.0, s);
+        fps_streaming_kernel<<<b, kFpsThreads, 0, s>>>(xyz, offset, new_offset, tmp, idx, logB);
+    }
     return check_launch("fps_streaming");
 }

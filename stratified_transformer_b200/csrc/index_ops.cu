@@ -86,6 +86,8 @@ int stb200_transpose_csr(int N, int M, const int *index0_offsets, const int *ind
     size_t tmp_bytes = sort_temp_bytes(N, M);
 
     const int blocks = max(1, min((N + 7) / 8, kNumSMs * 8));
+    KernelScope ks("transpose_csr[6 launches]", 4.0 * (N + 1) * 2 + 4.0 * M * 3, s);
+    count_launch(5);
     expand_index0_kernel<<<blocks, 256, 0, s>>>(N, index0_offsets, index0, iota);
     // stable LSD radix sort over the significant key bits only: within a key, pairs stay in ascending pair id
     cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, index1, sorted_keys, iota, t_pair, M, 0,
@@ -96,7 +98,6 @@ int stb200_transpose_csr(int N, int M, const int *index0_offsets, const int *ind
     }
     key_offsets_kernel<<<(N + 1 + 255) / 256, 256, 0, s>>>(N, M, sorted_keys, t_offsets);
     gather_int_kernel<<<max(1, min((M + 255) / 256, kNumSMs * 8)), 256, 0, s>>>(M, index0, t_pair, t_index0);
-    count_launch(6);
     return check_launch("transpose_csr");
 }
 

@@ -127,9 +127,11 @@ static int launch_pair(int D, const PairParams &p, cudaStream_t s) {
     if (p.M == 0) return STB200_OK;
     const long long threads = (long long)p.M * p.h * (D / 4);
     const int blocks = (int)max(1LL, min((threads + kLThreads - 1) / kLThreads, (long long)kNumSMs * 16));
-    if (D == 16) pair_kernel<16, OP><<<blocks, kLThreads, 0, s>>>(p);
-    else pair_kernel<32, OP><<<blocks, kLThreads, 0, s>>>(p);
-    count_launch();
+    {
+        KernelScope ks("pair_kernel[v1]", 0.0, s);
+        if (D == 16) pair_kernel<16, OP><<<blocks, kLThreads, 0, s>>>(p);
+        else pair_kernel<32, OP><<<blocks, kLThreads, 0, s>>>(p);
+    }
     return check_launch("pair_kernel");
 }
 

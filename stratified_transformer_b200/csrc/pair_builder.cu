@@ -400,6 +400,8 @@ int stb200_stratified_pairs_count(int N, int b, const float *xyz, const int *off
     carve(st, (char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255), N);
     const int has_sparse = m > 0;
     const int gb = blocks_for(N);
+    KernelScope ks("pair_builder_count[20 launches]", 0.0, s);
+    count_launch(19);
     init_state_kernel<<<gb, 256, 0, s>>>(st.mm, st.gp, st.ds_mask, N);
     minmax_kernel<<<blocks_for(N, 256, kNumSMs * 2), 256, 0, s>>>(N, xyz, st.mm);
     if (has_sparse) mark_sampled_kernel<<<blocks_for(m), 256, 0, s>>>(m, downsample_idx, st.ds_mask, N);
@@ -424,21 +426,24 @@ int stb200_stratified_pairs_count(int N, int b, const float *xyz, const int *off
     tb = st.cub_bytes;
     cub::DeviceScan::ExclusiveSum(st.cub_tmp, tb, st.counts, index0_offsets, N + 1, s);
     finish_count_kernel<<<1, 32, 0, s>>>(N, index0_offsets, st.gp, totals);
-    count_launch(20);
     return check_launch("stratified_pairs_count");
 }
 
 int stb200_stratified_pairs_fill(int N, const float *xyz, float window_size_x2, float quant_size, int has_sparse,
                                  void *workspace, size_t workspace_bytes, const int *index0_offsets, int *index_1,
-                                 int *rel_idx, int *index_0, void *stream) {
+                                 int *rel_idx, int *index_0, int M, void *stream) {
     STB200_REQUIRE(N > 0 && xyz && workspace && index0_offsets && index_1, STB200_ERR_ARG, "null pointer / bad N");
     STB200_REQUIRE(workspace_bytes >= stb200_pair_builder_workspace_bytes(N), STB200_ERR_WORKSPACE, "workspace too small");
     BuilderState st;
     carve(st, (char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255), N);
-    fill_pairs_kernel<<<blocks_for((long long)N * kWarp), 256, 0, (cudaStream_t)stream>>>(
-        N, xyz, index0_offsets, st.win_s, st.win_l, st.wstart_s, st.wstart_l, st.order_s, st.spos, st.samp, st.wc,
-        has_sparse, window_size_x2, quant_size, index_1, rel_idx, index_0);
-    count_launch();
+    {
+        // writes: index_1 (+ rel_idx, index_0); reads: xyz, offsets, window membership per point
+        const double bytes = (double)M * (4 + (rel_idx ? 12 : 0) + (index_0 ? 4 : 0)) + (double)N * (12 + 4 + 8 + 16);
+        KernelScope ks("pair_builder_fill", bytes, (cudaStream_t)stream);
+        fill_pairs_kernel<<<blocks_for((long long)N * kWarp), 256, 0, (cudaStream_t)stream>>>(
+            N, xyz, index0_offsets, st.win_s, st.win_l, st.wstart_s, st.wstart_l, st.order_s, st.spos, st.samp, st.wc,
+            has_sparse, window_size_x2, quant_size, index_1, rel_idx, index_0);
+    }
     return check_launch("stratified_pairs_fill");
 }
 
@@ -447,9 +452,11 @@ int stb200_rel_pos_index_stratified(int N, const float *xyz, const int *index0_o
     STB200_REQUIRE(N >= 0, STB200_ERR_ARG, "bad N");
     if (N == 0) return STB200_OK;
     STB200_REQUIRE(xyz && index0_offsets && index_1 && rel_idx, STB200_ERR_ARG, "null pointer");
-    rel_index_csr_kernel<<<blocks_for((long long)N * kWarp), 256, 0, (cudaStream_t)stream>>>(
-        N, xyz, index0_offsets, index_1, window_size_x2, quant_size, rel_idx);
-    count_launch();
+    {
+        KernelScope ks("rel_pos_index_stratified", 0.0, (cudaStream_t)stream);
+        rel_index_csr_kernel<<<blocks_for((long long)N * kWarp), 256, 0, (cudaStream_t)stream>>>(
+            N, xyz, index0_offsets, index_1, window_size_x2, quant_size, rel_idx);
+    }
     return check_launch("rel_pos_index_stratified");
 }
 
@@ -460,13 +467,14 @@ int stb200_rel_pos_index_swin(int N, const float *xyz, const int *index0_offsets
     if (N == 0) return STB200_OK;
     STB200_REQUIRE(xyz && index0_offsets && index_1 && rel_idx && xq_scratch && mm_scratch, STB200_ERR_ARG, "null pointer");
     cudaStream_t s = (cudaStream_t)stream;
+    KernelScope ks("rel_pos_index_swin[3 launches]", 0.0, s);
+    count_launch(2);
     cudaMemsetAsync(mm_scratch, 0xff, 3 * sizeof(unsigned), s);
     cudaMemsetAsync(mm_scratch + 3, 0, 3 * sizeof(unsigned), s);
     minmax_kernel<<<blocks_for(N, 256, kNumSMs * 2), 256, 0, s>>>(N, xyz, mm_scratch);
     swin_quant_kernel<<<blocks_for((long long)N * 3), 256, 0, s>>>(N, xyz, mm_scratch, shift_size, window_size, quant_size, xq_scratch);
     swin_rel_kernel<<<blocks_for((long long)N * kWarp), 256, 0, s>>>(N, xq_scratch, index0_offsets, index_1,
                                                                     (float)(quant_grid_length - 1), rel_idx);
-    count_launch(3);
     return check_launch("rel_pos_index_swin");
 }
 

@@ -86,7 +86,7 @@ def build_stratified_index(xyz: torch.Tensor, offset: torch.Tensor, window_size:
                    float(quant_size if quant_size is not None else 1.0), int(m > 0), workspace.data_ptr(),
                    workspace.numel(), offsets.data_ptr(), index_1.data_ptr(),
                    None if rel_idx is None else rel_idx.data_ptr(), None if index_0 is None else index_0.data_ptr(),
-                   _stream())
+                   M, _stream())
     return PairIndex(offsets, index_1, rel_idx, int(n_max), int(M), index_0)
 
 

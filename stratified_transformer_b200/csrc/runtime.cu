@@ -85,6 +85,7 @@ void stb200_profile_enable(int on) {
 size_t stb200_profile_dump(char *buf, size_t cap) {
     using namespace stb200;
     std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!buf || !cap) return 320 * (g_prof.size() + 1);  // size query only: upper bound, records are kept
     struct Agg { long long n = 0; double ms = 0, bytes = 0; };
     std::map<std::string, Agg> agg;
     for (auto &r : g_prof) {

@@ -16,6 +16,8 @@
 // winner's coordinates travel with the candidate record so no global load sits on the critical path.
 #include <cooperative_groups.h>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -23,7 +25,7 @@ namespace cg = cooperative_groups;
 
 namespace stb200 {
 
-constexpr int kFpsThreads = 1024;
+constexpr int kFpsThreads = 256;   // few warps per CTA: the per-iteration exchange cost grows with the warp count
 constexpr int kMaxCluster = 16;
 
 struct __align__(16) FpsRec {
@@ -51,22 +53,90 @@ __device__ __forceinline__ void warp_argmax(unsigned &key, unsigned &rank) {
     key = kmax;
 }
 
-template <int P, bool CLUSTER>
-__global__ void __launch_bounds__(kFpsThreads, 1)
+// ---- mbarrier / DSMEM primitives (PTX) ---------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ unsigned map_to_cta(unsigned local_addr, unsigned cta) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
+    return r;
+}
+// remote shared-memory store that also completes `bytes` on the destination CTA's mbarrier
+__device__ __forceinline__ void st_async_v4(unsigned raddr, unsigned a, unsigned b, unsigned c, unsigned d, unsigned rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr),
+                 "r"(a), "r"(b), "r"(c), "r"(d), "r"(rbar)
+                 : "memory");
+}
+__device__ __forceinline__ void st_async_b32(unsigned raddr, unsigned a, unsigned rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(raddr), "r"(a), "r"(rbar)
+                 : "memory");
+}
+
+// (key, rank) -> warp winner; returns the winning lane.  Exact ties on the distance are rare (continuous
+// coordinates), so the rank reduction only runs when the ballot shows more than one lane at the maximum.
+__device__ __forceinline__ int warp_argmax_lane(unsigned key, unsigned rank) {
+    const unsigned kmax = __reduce_max_sync(0xffffffffu, key);
+    unsigned bal = __ballot_sync(0xffffffffu, key == kmax);
+    if (__popc(bal) > 1) {
+        const unsigned rmin = __reduce_min_sync(0xffffffffu, key == kmax ? rank : 0xffffffffu);
+        bal = __ballot_sync(0xffffffffu, key == kmax && rank == rmin);
+    }
+    return __ffs(bal) - 1;
+}
+
+// One iteration, per warp (no __syncthreads, no hardware cluster barrier inside the loop):
+//   1. every thread updates its P running minima and keeps its best candidate;
+//   2. redux argmax in the warp; the winner's record {key, rank, x, y, z} is shuffled to lanes 0..cs-1 and lane c
+//      sends it with st.async (data + complete_tx) into slot [crank * nwarps + warp] of CTA c's inbox;
+//   3. every warp waits on its own CTA's inbox mbarrier (armed by thread 0 with expect_tx for cs * nwarps records),
+//      reduces the cs * nwarps records and continues with the global winner's coordinates.
+// Inbox and mbarrier are double-buffered: a CTA cannot run two iterations ahead of a peer because it needs that
+// peer's records of the next iteration first.
+constexpr int kMaxRecords = 512;  // cluster_size * warps per CTA
+
+template <int P, bool CLUSTER, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
 fps_kernel(const float *__restrict__ xyz, const int *__restrict__ offset, const int *__restrict__ new_offset,
-           int *__restrict__ idx, int logB, int cluster_size) {
+           int *__restrict__ idx, int logB, int cluster_size, long long *dbg) {
     extern __shared__ float sxyz[];  // [3][P * T] coordinates of this CTA's points, for winner look-up
-    __shared__ unsigned wkey[2][32], wrank[2][32];
-    __shared__ FpsRec crec[2][kMaxCluster];
+    __shared__ uint4 inbox_a[2][kMaxRecords];   // key, rank, x, y
+    __shared__ float inbox_z[2][kMaxRecords];
+    __shared__ __align__(8) unsigned long long cbar[2];
 
     const int T = blockDim.x, tid = threadIdx.x, lane = tid % kWarp, warp = tid / kWarp, nwarps = T / kWarp;
     const int crank = CLUSTER ? (int)cg::this_cluster().block_rank() : 0;
     const int scene = blockIdx.x / cluster_size;
     const int TT = T * cluster_size, gtid = crank * T + tid;
+    const int nrec = cluster_size * nwarps;
 
     const int start_n = scene ? offset[scene - 1] : 0, n = offset[scene] - start_n;
     const int start_m = scene ? new_offset[scene - 1] : 0, m = new_offset[scene] - start_m;
 
+    if (tid == 0) {
+        mbar_init(smem_u32(&cbar[0]), 1);
+        mbar_init(smem_u32(&cbar[1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     float px[P], py[P], pz[P], mind[P];
 #pragma unroll
     for (int u = 0; u < P; ++u) {
@@ -87,11 +157,28 @@ fps_kernel(const float *__restrict__ xyz, const int *__restrict__ offset, const 
         oz = xyz[(size_t)start_n * 3 + 2];
     }
     if (gtid == 0 && m > 0) idx[start_m] = start_n;
+    // destination of this lane's sends: slot of (this CTA, this warp) in the inbox of CTA `lane`
+    unsigned dst_a[2] = {0, 0}, dst_z[2] = {0, 0}, dst_bar[2] = {0, 0};
+    if (lane < cluster_size) {
+#pragma unroll
+        for (int bf = 0; bf < 2; ++bf) {
+            dst_a[bf] = map_to_cta(smem_u32(&inbox_a[bf][crank * nwarps + warp]), (unsigned)lane);
+            dst_z[bf] = map_to_cta(smem_u32(&inbox_z[bf][crank * nwarps + warp]), (unsigned)lane);
+            dst_bar[bf] = map_to_cta(smem_u32(&cbar[bf]), (unsigned)lane);
+        }
+    }
     __syncthreads();
-    if (CLUSTER) cg::this_cluster().sync();  // every CTA of the cluster is resident before remote stores
+    if (CLUSTER) cg::this_cluster().sync();  // barriers initialised and every CTA resident before any remote store
 
-    int buf = 0;
-    for (int j = 1; j < m; ++j, buf ^= 1) {
+    const unsigned tx_bytes = 20u * (unsigned)nrec;
+    for (int j = 1; j < m; ++j) {
+        const int buf = j & 1;
+        const unsigned parity = (unsigned)((j - 1) >> 1) & 1u;  // k-th use of this buffer, k = (j-1)/2
+        if (tid == 0) mbar_arrive_expect_tx(smem_u32(&cbar[buf]), tx_bytes);
+        // development aid: per-phase clock stamps of warps 0 and 1 of CTA 0 for iterations 64..79
+        const bool stamp = dbg && blockIdx.x == 0 && lane == 0 && warp < 2 && j >= 64 && j < 80;
+        long long *ds = dbg + ((j - 64) * 2 + warp) * 8;
+        if (stamp) ds[0] = clock64();
         float best = -2.f;
         int bu = 0;
 #pragma unroll
@@ -106,61 +193,50 @@ fps_kernel(const float *__restrict__ xyz, const int *__restrict__ offset, const 
             }
         }
         // distances are >= 0: their bit patterns order like unsigned ints; 0 is reserved for "no point"
-        unsigned key = best >= 0.f ? __float_as_uint(best) + 1u : 0u;
-        unsigned rank = fps_rank(gtid + bu * TT, logB);
-        warp_argmax(key, rank);
-        if (lane == 0) {
-            wkey[buf][warp] = key;
-            wrank[buf][warp] = rank;
-        }
-        __syncthreads();
-        key = lane < nwarps ? wkey[buf][lane] : 0u;
-        rank = lane < nwarps ? wrank[buf][lane] : 0xffffffffu;
-        warp_argmax(key, rank);  // every warp now knows the CTA winner
-
-        int win;
-        if (CLUSTER) {
-            if (tid < cluster_size) {
-                FpsRec r;
-                r.key = key;
-                r.rank = rank;
-                const int i = fps_unrank(rank, logB);
-                const int slot = ((i - crank * T) / TT) * T + (i - crank * T) % TT;  // u * T + tid of the owner
-                const bool mine = key != 0u && i >= crank * T && (i - crank * T) % TT < T;
-                r.x = mine ? sxyz[0 * P * T + slot] : 0.f;
-                r.y = mine ? sxyz[1 * P * T + slot] : 0.f;
-                r.z = mine ? sxyz[2 * P * T + slot] : 0.f;
-                r.pad[0] = r.pad[1] = r.pad[2] = 0u;
-                FpsRec *dst = cg::this_cluster().map_shared_rank(&crec[buf][crank], tid);
-                *dst = r;
+        const unsigned key = best >= 0.f ? __float_as_uint(best) + 1u : 0u;
+        const unsigned rank = fps_rank(gtid + bu * TT, logB);
+        if (stamp) ds[1] = clock64();
+        {
+            const int src = warp_argmax_lane(key, rank);
+            const int slot = bu * T + tid;
+            const unsigned wk = __shfl_sync(0xffffffffu, key, src), wr = __shfl_sync(0xffffffffu, rank, src);
+            const int wslot = __shfl_sync(0xffffffffu, slot, src);
+            if (lane < cluster_size) {
+                const float wx = sxyz[0 * P * T + wslot], wy = sxyz[1 * P * T + wslot], wz = sxyz[2 * P * T + wslot];
+                st_async_v4(dst_a[buf], wk, wr, __float_as_uint(wx), __float_as_uint(wy), dst_bar[buf]);
+                st_async_b32(dst_z[buf], __float_as_uint(wz), dst_bar[buf]);
             }
-            cg::this_cluster().sync();
-            const FpsRec r = crec[buf][lane < cluster_size ? lane : 0];
-            unsigned k2 = lane < cluster_size ? r.key : 0u;
-            unsigned r2 = lane < cluster_size ? r.rank : 0xffffffffu;
-            const unsigned myk = k2, myr = r2;
-            warp_argmax(k2, r2);
-            const unsigned who = __ballot_sync(0xffffffffu, lane < cluster_size && myk == k2 && myr == r2);
-            const int src = __ffs(who) - 1;
-            ox = __shfl_sync(0xffffffffu, r.x, src);
-            oy = __shfl_sync(0xffffffffu, r.y, src);
-            oz = __shfl_sync(0xffffffffu, r.z, src);
-            win = fps_unrank(r2, logB);
-        } else {
-            win = fps_unrank(rank, logB);
-            const int slot = (win / T) * T + win % T;
-            ox = sxyz[0 * P * T + slot];
-            oy = sxyz[1 * P * T + slot];
-            oz = sxyz[2 * P * T + slot];
         }
-        if (gtid == 0) idx[start_m + j] = start_n + win;
+        if (stamp) ds[2] = clock64();
+        mbar_wait(smem_u32(&cbar[buf]), parity);
+        if (stamp) ds[3] = clock64();
+        {
+            unsigned bk = 0u, br = 0xffffffffu;
+            int bi = 0;
+            for (int r = lane; r < nrec; r += kWarp) {
+                const uint4 a = inbox_a[buf][r];
+                if (a.x > bk || (a.x == bk && a.y < br)) {
+                    bk = a.x;
+                    br = a.y;
+                    bi = r;
+                }
+            }
+            const int src = warp_argmax_lane(bk, br);
+            const int wi = __shfl_sync(0xffffffffu, bi, src);
+            const uint4 a = inbox_a[buf][wi];
+            ox = __uint_as_float(a.z);
+            oy = __uint_as_float(a.w);
+            oz = inbox_z[buf][wi];
+            if (gtid == 0) idx[start_m + j] = start_n + fps_unrank(a.y, logB);
+        }
+        if (stamp) ds[4] = clock64();
     }
     if (CLUSTER) cg::this_cluster().sync();  // no CTA exits while a peer may still write into its smem
 }
 
 // Fallback for scenes too large for the register-resident kernel: one CTA per scene, coordinates and running
 // minima streamed from global memory (the caller's `tmp` scratch), same (max distance, min rank) reduction.
-__global__ void __launch_bounds__(kFpsThreads, 1)
+__global__ void __launch_bounds__(1024, 1)
 fps_streaming_kernel(const float *__restrict__ xyz, const int *__restrict__ offset, const int *__restrict__ new_offset,
                      float *__restrict__ tmp, int *__restrict__ idx, int logB) {
     __shared__ unsigned wkey[2][32], wrank[2][32];
@@ -214,21 +290,23 @@ static int ref_block_log2(int n) {
     return pow_2;
 }
 
-template <int P>
-static int launch_fps(int b, int cs, const float *xyz, const int *offset, const int *new_offset, int *idx, int logB,
-                      cudaStream_t s) {
-    const size_t smem = (size_t)3 * P * kFpsThreads * sizeof(float);
+constexpr int kFpsRetrySmallerCluster = -1;
+static long long *g_fps_dbg = nullptr;  // development aid, see stb200_fps_debug_buffer
+
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+template <int P, int MAXT = (P <= 8 ? 1024 : (P <= 20 ? 512 : 256))>  // register budget: 4 P + ~40 per thread
+static int launch_fps(int b, int cs, int threads, const float *xyz, const int *offset, const int *new_offset, int *idx,
+                      int logB, cudaStream_t s) {
+    STB200_REQUIRE(threads <= MAXT && threads % 32 == 0, STB200_ERR_ARG, "fps: %d threads with %d points per thread", threads, P);
+    const size_t smem = (size_t)3 * P * threads * sizeof(float);
     cudaError_t e;
     KernelScope ks("fps_cluster", 0.0, s);  // latency-bound by construction: bytes are not the meaningful unit
-    if (cs == 1) {
-        auto kern = fps_kernel<P, false>;
-        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) {
-            set_error("fps smem attr: %s", cudaGetErrorString(e));
-            return STB200_ERR_CUDA;
-        }
-        kern<<<b, kFpsThreads, smem, s>>>(xyz, offset, new_offset, idx, logB, 1);
-    } else {
-        auto kern = fps_kernel<P, true>;
+    {
+        auto kern = fps_kernel<P, true, MAXT>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess ||
             (e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)) != cudaSuccess) {
             set_error("fps attr: %s", cudaGetErrorString(e));
@@ -236,7 +314,7 @@ static int launch_fps(int b, int cs, const float *xyz, const int *offset, const 
         }
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(b * cs);
-        cfg.blockDim = dim3(kFpsThreads);
+        cfg.blockDim = dim3(threads);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = s;
         cudaLaunchAttribute attr[1];
@@ -246,7 +324,17 @@ static int launch_fps(int b, int cs, const float *xyz, const int *offset, const 
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        if ((e = cudaLaunchKernelEx(&cfg, kern, xyz, offset, new_offset, idx, logB, cs)) != cudaSuccess) {
+        if (cs > 1) {   // all scenes must be co-resident, otherwise the clusters run in waves: retry with a smaller cluster
+            int max_clusters = 0;
+            const cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
+            if (getenv("STB200_FPS_DEBUG"))
+                fprintf(stderr, "[stb200 fps] b=%d cluster=%d threads=%d P=%d smem=%zu -> max active clusters %d (%s)\n", b, cs,
+                        threads, P, smem, max_clusters, cudaGetErrorString(oe));
+            if (oe == cudaSuccess && max_clusters < b &&
+                max_clusters * 2 > 0 && (b + max_clusters - 1) / max_clusters > (b * (cs / 2) > kNumSMs ? 2 : 1))
+                return kFpsRetrySmallerCluster;
+        }
+        if ((e = cudaLaunchKernelEx(&cfg, kern, xyz, offset, new_offset, idx, logB, cs, g_fps_dbg)) != cudaSuccess) {
             set_error("fps cluster launch (cluster=%d): %s", cs, cudaGetErrorString(e));
             return STB200_ERR_CUDA;
         }
@@ -258,6 +346,8 @@ static int launch_fps(int b, int cs, const float *xyz, const int *offset, const 
 
 using namespace stb200;
 
+extern "C" void stb200_fps_debug_buffer(long long *device_buffer /* >= 16*2*8 int64, or NULL */) { g_fps_dbg = device_buffer; }
+
 extern "C" int stb200_furthestsampling(int b, int n, const float *xyz, const int *offset, const int *new_offset,
                                        float *tmp, int *idx, void *stream) {
     STB200_REQUIRE(b >= 0 && n >= 0, STB200_ERR_ARG, "bad sizes b=%d n=%d", b, n);
@@ -267,20 +357,36 @@ extern "C" int stb200_furthestsampling(int b, int n, const float *xyz, const int
     cudaStream_t s = (cudaStream_t)stream;
     const int logB = ref_block_log2(n);
     // cluster size: as many CTAs per scene as keep all scenes co-resident (148 SMs), but never more threads than points
-    int cs = kMaxCluster;
-    while (cs > 1 && (b * cs > kNumSMs || (cs / 2) * kFpsThreads >= n)) cs >>= 1;
-    const int need = (n + cs * kFpsThreads - 1) / (cs * kFpsThreads);
-    if (need <= 1) return launch_fps<1>(b, cs, xyz, offset, new_offset, idx, logB, s);
-    if (need <= 2) return launch_fps<2>(b, cs, xyz, offset, new_offset, idx, logB, s);
-    if (need <= 3) return launch_fps<3>(b, cs, xyz, offset, new_offset, idx, logB, s);
-    if (need <= 4) return launch_fps<4>(b, cs, xyz, offset, new_offset, idx, logB, s);
-    if (need <= 5) return launch_fps<5>(b, cs, xyz, offset, new_offset, idx, logB, s);
-    if (need <= 6) return launch_fps<6>(b, cs, xyz, offset, new_offset, idx, logB, s);
-    if (need <= 8) return launch_fps<8>(b, cs, xyz, offset, new_offset, idx, logB, s);
+    // tuning overrides (development): STB200_FPS_CLUSTER caps the cluster size, STB200_FPS_THREADS sets the CTA size
+    // large scenes: 128-thread CTAs in clusters of 16 (measured faster than 256 x 8); otherwise 256 threads
+    const int threads = env_int("STB200_FPS_THREADS", n > 16 * kFpsThreads * 12 ? 128 : kFpsThreads);
+    const int per_thread = env_int("STB200_FPS_POINTS", 10);   // target points per thread when choosing the cluster size
+    int cs = 1;
+    while (cs < env_int("STB200_FPS_CLUSTER", kMaxCluster) && b * cs * 2 <= kNumSMs && cs * threads * per_thread < n) cs <<= 1;
+    for (; cs >= 1; cs >>= 1) {
+        const int need = (n + cs * threads - 1) / (cs * threads);
+        int rc = STB200_ERR_ARG;
+        if (need <= 1) rc = launch_fps<1>(b, cs, threads, xyz, offset, new_offset, idx, logB, s);
+        else if (need <= 2) rc = launch_fps<2>(b, cs, threads, xyz, offset, new_offset, idx, logB, s);
+        else if (need <= 3) rc = launch_fps<3>(b, cs, threads, xyz, offset, new_offset, idx, logB, s);
+        else if (need <= 4) rc = launch_fps<4>(b, cs, threads, xyz, offset, new_offset, idx, logB, s);
+        else if (need <= 5) rc = launch_fps<5>(b, cs, threads, xyz, offset, new_offset, idx, logB, s);
+        else if (need <= 6) rc = launch_fps<6>(b, cs, threads, xyz, offset, new_offset, idx, logB, s);
+        else if (need <= 8) rc = launch_fps<8>(b, cs, threads, xyz, offset, new_offset, idx, logB, s);
+        else if (need <= 10) rc = launch_fps<10>(b, cs, threads, xyz, offset, new_offset, idx, logB, s);
+        else if (need <= 12) rc = launch_fps<12>(b, cs, threads, xyz, offset, new_offset, idx, logB, s);
+        else if (need <= 16) rc = launch_fps<16>(b, cs, threads, xyz, offset, new_offset, idx, logB, s);
+        else if (need <= 20) rc = launch_fps<20>(b, cs, threads, xyz, offset, new_offset, idx, logB, s);
+        else if (need <= 24) rc = launch_fps<24>(b, cs, threads, xyz, offset, new_offset, idx, logB, s);
+        else if (need <= 32) rc = launch_fps<32>(b, cs, threads, xyz, offset, new_offset, idx, logB, s);
+        else if (need <= 40) rc = launch_fps<40>(b, cs, threads, xyz, offset, new_offset, idx, logB, s);
+        else break;   // too many points per thread for the register-resident kernel
+        if (rc != kFpsRetrySmallerCluster) return rc;
+    }
     STB200_REQUIRE(tmp, STB200_ERR_ARG, "scene of %d points needs the tmp scratch (streaming path)", n);
     {
         KernelScope ks("fps_streaming", 0.0, s);
-        fps_streaming_kernel<<<b, kFpsThreads, 0, s>>>(xyz, offset, new_offset, tmp, idx, logB);
+        fps_streaming_kernel<<<b, 1024, 0, s>>>(xyz, offset, new_offset, tmp, idx, logB);
     }
     return check_launch("fps_streaming");
 }

@@ -58,6 +58,14 @@ __device__ __forceinline__ void stage_table(float *dst, const float *__restrict_
 
 __device__ __forceinline__ int clampi(int v, int hi) { return min(max(v, 0), hi); }
 
+constexpr int kUnroll = 4;  // independent row gathers kept in flight per lane
+
+// the three rel-pos bins of one pair, clamped to [0, L) and packed 10 bits each (L <= 1024)
+__device__ __forceinline__ unsigned pack_bins(const int *__restrict__ r, int L) {
+    const unsigned r0 = clampi(ld_stream(r + 0), L - 1), r1 = clampi(ld_stream(r + 1), L - 1), r2 = clampi(ld_stream(r + 2), L - 1);
+    return r0 | (r1 << 10) | (r2 << 20);
+}
+
 // E[c..c+3] = (T[0][r0] + T[1][r1]) + T[2][r2] for one head chunk (left-to-right adds like the reference)
 template <int D, int HG>
 __device__ __forceinline__ float4 table_sum4(const float *ts, int L, int r0, int r1, int r2, int hh, int g) {
@@ -102,27 +110,45 @@ __global__ void __launch_bounds__(kThreads) seg_dot_kernel(const SegParams p) {
             __syncwarp();
             for (int i = lane; i < HG * G; i += kWarp) xw[i] = ld_row4(p.X + (size_t)n * C + h0 * D + 4 * i);
             __syncwarp();
-            const int items = len * HG;
-            for (int base = 0; base < items; base += NS) {
-                const int e = base + grp;
-                const bool active = e < items;
-                const int ee = active ? e : items - 1;
-                const int pair = ee / HG, hh = ee - pair * HG;
-                const int m = start + pair;
-                const int j = ld_stream(p.gather_idx + m);
-                const float4 x4 = xw[hh * G + g];
-                const float4 y4 = ld_row4(p.Y + (size_t)j * C + (h0 + hh) * D + 4 * g);
-                float acc = 0.f;
-                if (XY) acc = f4_dot(x4, y4, acc);
-                if (EX || EY) {
-                    const int r0 = clampi(ld_stream(p.rel_idx + 3 * (size_t)m + 0), L - 1);
-                    const int r1 = clampi(ld_stream(p.rel_idx + 3 * (size_t)m + 1), L - 1);
-                    const int r2 = clampi(ld_stream(p.rel_idx + 3 * (size_t)m + 2), L - 1);
-                    if (EX) acc = f4_dot(x4, table_sum4<D, HG>(tx, L, r0, r1, r2, hh, g), acc);
-                    if (EY) acc = f4_dot(y4, table_sum4<D, HG>(ty, L, r0, r1, r2, hh, g), acc);
+            // 32 pairs at a time: one coalesced load of the key ids (and the packed rel-pos bins) per chunk,
+            // handed to the lane groups with shuffles; kUnroll independent row gathers in flight per lane.
+            for (int c0 = 0; c0 < len; c0 += kWarp) {
+                const int cnt = min(kWarp, len - c0);
+                const int mt = start + c0 + min(lane, cnt - 1);
+                const int j_l = ld_stream(p.gather_idx + mt);
+                unsigned pk_l = 0;
+                if (EX || EY) pk_l = pack_bins(p.rel_idx + 3 * (size_t)mt, L);
+                const int items = cnt * HG;
+                for (int e0 = 0; e0 < items; e0 += NS * kUnroll) {
+                    float4 y4[kUnroll];
+                    int pl[kUnroll], hh[kUnroll];
+                    bool act[kUnroll];
+#pragma unroll
+                    for (int u = 0; u < kUnroll; ++u) {
+                        const int e = e0 + u * NS + grp;
+                        act[u] = e < items;
+                        const int ee = act[u] ? e : items - 1;
+                        pl[u] = ee / HG;
+                        hh[u] = ee - pl[u] * HG;
+                        const int j = __shfl_sync(0xffffffffu, j_l, pl[u]);
+                        y4[u] = ld_row4(p.Y + (size_t)j * C + (h0 + hh[u]) * D + 4 * g);
+                    }
+#pragma unroll
+                    for (int u = 0; u < kUnroll; ++u) {
+                        if (e0 + u * NS >= items) break;   // warp-uniform
+                        const float4 x4 = xw[hh[u] * G + g];
+                        float acc = 0.f;
+                        if (XY) acc = f4_dot(x4, y4[u], acc);
+                        if (EX || EY) {
+                            const unsigned pk = __shfl_sync(0xffffffffu, pk_l, pl[u]);
+                            const int r0 = pk & 0x3ff, r1 = (pk >> 10) & 0x3ff, r2 = pk >> 20;
+                            if (EX) acc = f4_dot(x4, table_sum4<D, HG>(tx, L, r0, r1, r2, hh[u], g), acc);
+                            if (EY) acc = f4_dot(y4[u], table_sum4<D, HG>(ty, L, r0, r1, r2, hh[u], g), acc);
+                        }
+                        acc = group_sum<G>(acc);
+                        if (act[u] && g == 0) p.out[(size_t)(start + c0 + pl[u]) * h + h0 + hh[u]] = acc;
+                    }
                 }
-                acc = group_sum<G>(acc);
-                if (active && g == 0) p.out[(size_t)m * h + h0 + hh] = acc;
             }
         }
     }
@@ -158,22 +184,39 @@ __global__ void __launch_bounds__(kThreads) seg_reduce_kernel(const SegParams p)
             float4 acc[HG];
 #pragma unroll
             for (int hh = 0; hh < HG; ++hh) acc[hh] = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int t = start + slot; t < end; t += NS) {
-                const int m = PERM ? ld_stream(p.pair_id + t) : t;
-                const int j = HAS_Y ? ld_stream(p.gather_idx + t) : 0;
-                int r0 = 0, r1 = 0, r2 = 0;
-                if (HAS_T) {
-                    r0 = clampi(ld_stream(p.rel_idx + 3 * (size_t)m + 0), L - 1);
-                    r1 = clampi(ld_stream(p.rel_idx + 3 * (size_t)m + 1), L - 1);
-                    r2 = clampi(ld_stream(p.rel_idx + 3 * (size_t)m + 2), L - 1);
-                }
+            for (int c0 = start; c0 < end; c0 += kWarp) {
+                const int cnt = min(kWarp, end - c0);
+                const int tl = c0 + min(lane, cnt - 1);
+                const int m_l = PERM ? ld_stream(p.pair_id + tl) : tl;
+                const int j_l = HAS_Y ? ld_stream(p.gather_idx + tl) : 0;
+                unsigned pk_l = 0;
+                if (HAS_T) pk_l = pack_bins(p.rel_idx + 3 * (size_t)m_l, L);
+                constexpr int U = 2;   // pair slots per lane group in flight (U * HG row gathers)
+                for (int s0 = 0; s0 < cnt; s0 += NS * U) {
+                    float4 val[U][HG];
+                    float wv[U][HG];
+                    bool act[U];
 #pragma unroll
-                for (int hh = 0; hh < HG; ++hh) {
-                    const float wv = ld_stream(p.w + (size_t)m * h + h0 + hh);
-                    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (HAS_T) val = table_sum4<D, HG>(ts, L, r0, r1, r2, hh, g);
-                    if (HAS_Y) val = f4_add(val, ld_row4(p.Y + (size_t)j * C + (h0 + hh) * D + 4 * g));
-                    acc[hh] = f4_fma(wv, val, acc[hh]);
+                    for (int u = 0; u < U; ++u) {
+                        const int pl = s0 + u * NS + slot;
+                        act[u] = pl < cnt;
+                        const int pc = act[u] ? pl : cnt - 1;
+                        const int m = PERM ? __shfl_sync(0xffffffffu, m_l, pc) : c0 + pc;
+                        const int j = HAS_Y ? __shfl_sync(0xffffffffu, j_l, pc) : 0;
+                        const unsigned pk = HAS_T ? __shfl_sync(0xffffffffu, pk_l, pc) : 0u;
+                        const int r0 = pk & 0x3ff, r1 = (pk >> 10) & 0x3ff, r2 = pk >> 20;
+#pragma unroll
+                        for (int hh = 0; hh < HG; ++hh) {
+                            wv[u][hh] = act[u] ? ld_stream(p.w + (size_t)m * h + h0 + hh) : 0.f;
+                            val[u][hh] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (HAS_Y) val[u][hh] = ld_row4(p.Y + (size_t)j * C + (h0 + hh) * D + 4 * g);
+                            if (HAS_T) val[u][hh] = f4_add(table_sum4<D, HG>(ts, L, r0, r1, r2, hh, g), val[u][hh]);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+#pragma unroll
+                        for (int hh = 0; hh < HG; ++hh) acc[hh] = f4_fma(wv[u][hh], val[u][hh], acc[hh]);
                 }
             }
 #pragma unroll
@@ -199,92 +242,150 @@ __global__ void __launch_bounds__(kThreads) seg_reduce_kernel(const SegParams p)
 
 // ------------------------------------------------------------------------------------------------
 // table_grad: gT[l, h, c, a] += sum_n X[n, h, c] * W_a[n, l],  W_a[n, l] = sum_{t in seg(n), rel_idx[m(t), a] = l} w[m(t), h]
-// grid = (persistent tiles, h).  Per tile of TQ rows: phase A builds the TQ histograms in shared memory with one
-// thread per (row, axis) (private column, no atomics); phase B accumulates the outer products in registers.
-constexpr int kTQ = 64;       // rows per tile
-constexpr int kTQP = kTQ + 4; // padded row pitch of W: conflict-free LDS.128 for 8 consecutive table rows
+//
+// The reference issues 3*d float atomics per pair-head onto the 2*9216 table addresses.  Here the sum is split
+// into a per-row histogram (3 scalar adds per pair-head, no atomics) and a dense product with the row matrix:
+//   grid = (persistent tiles of TQ rows, head groups).  Per tile:
+//     A0  stage the tile's pairs, PC at a time: packed bins + the weights of all heads of the group, one
+//         round trip to memory per chunk with every thread issuing independent loads;
+//     A1  one thread per (head, axis, row) adds its row's weights into its private column of
+//         W[head][(axis, l)][row] in shared memory (no atomics);
+//     B   per head: C[(axis,l), c] += W^T X on the tensor cores: mma.sync m16n8k8 TF32 with the 3-term split
+//         (hi*hi + hi*lo + lo*hi), i.e. fp32-level accuracy; accumulators stay in registers across all tiles;
+//   one red.global.add per accumulator element at the end of the CTA.
+constexpr int kTQ = 32;        // rows per tile
+constexpr int kTQP = kTQ + 4;  // pitch of W rows: conflict-free A-fragment loads
+constexpr int kPC = 1024;      // pairs staged per chunk
+// one thread per (head, axis, row) in the histogram phase
+__host__ __device__ constexpr int kTGThreads(int hgc) { return hgc * 3 * kTQ < 128 ? 128 : hgc * 3 * kTQ; }
 
-template <int D, int RPT, bool PERM>
-__global__ void __launch_bounds__(kThreads) table_grad_kernel(const SegParams p, int row_pass_base) {
+// 3xTF32 operand split.  The tensor core reads only the top 19 bits of a tf32 operand, i.e. it truncates: so the
+// high part is the raw fp32 word, and the low part is x - trunc(x) (exact in fp32), again passed raw.  Two
+// instructions per element (cvt.rna.tf32 is a ~5-instruction emulation on sm_100a and dominated the first version).
+__device__ __forceinline__ void split_tf32(float x, unsigned &hi, unsigned &lo) {
+    hi = __float_as_uint(x);
+    lo = __float_as_uint(x - __uint_as_float(hi & 0xffffe000u));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int D, int HGC, bool PERM, bool MULTI>
+__global__ void __launch_bounds__(kTGThreads(HGC), (D == 16 ? 2 : 1)) table_grad_kernel(const SegParams p, int row_pass_base, int Rpad) {
     extern __shared__ float4 smem4[];
-    constexpr int G = D / 4;
-    constexpr int NL = kThreads / G;  // threads along the (axis, l) dimension
+    constexpr int NT = D / 8;                               // n-tiles (8 channels each)
+    constexpr int NW = kTGThreads(HGC) / kWarp;             // warps
+    constexpr int TPW = (16 * NT + NW - 1) / NW;            // (m-tile, n-tile) pairs per warp (<= 256 table rows per pass)
+    constexpr int XP = D + 8;                               // pitch of the X tile: conflict-free B-fragment loads
     const int L = p.L, h = p.h, R = 3 * L;
-    const int hh = blockIdx.y;
-    float *W = reinterpret_cast<float *>(smem4);              // [R][kTQP]
-    float4 *Xs = reinterpret_cast<float4 *>(W + R * kTQP);    // [kTQ][G]
-    const int tid = threadIdx.x;
-    const int cb = tid % G, lrow = tid / G;
+    const int Rp = min(256, R - row_pass_base);             // table rows handled in this pass
+    const int n_mt = (Rp + 15) / 16;
+    const int h0 = blockIdx.y * HGC;
+    float *W = reinterpret_cast<float *>(smem4);            // [HGC][Rpad][kTQP]
+    float *Xs = W + HGC * Rpad * kTQP;                      // [HGC][kTQ][XP]
+    float *sw = Xs + HGC * kTQ * XP;                        // [HGC][kPC] weights
+    unsigned *pk = reinterpret_cast<unsigned *>(sw + HGC * kPC);   // [kPC] r0 | r1<<8 | r2<<16
+    int *soff = reinterpret_cast<int *>(pk + kPC);          // [kTQ + 1] offsets of the tile's rows
+    const int tid = threadIdx.x, lane = tid % kWarp, warp = tid / kWarp, nthr = blockDim.x;
+    const int gid = lane >> 2, tig = lane & 3;
 
-    float4 acc[RPT];
+    float acc[HGC][TPW][4];
 #pragma unroll
-    for (int k = 0; k < RPT; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int a = 0; a < HGC; ++a)
+#pragma unroll
+        for (int b = 0; b < TPW; ++b)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
 
     for (int base_n = blockIdx.x * kTQ; base_n < p.N; base_n += gridDim.x * kTQ) {
-        __syncthreads();  // previous tile's phase B done
-        for (int i = tid; i < R * kTQP; i += kThreads) W[i] = 0.f;
-        for (int i = tid; i < kTQ * G; i += kThreads) {
-            const int n = base_n + i / G;
-            Xs[i] = n < p.N ? ld_row4(p.X + ((size_t)n * h + hh) * D + 4 * (i % G)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        __syncthreads();
-        if (tid < 3 * kTQ) {
-            const int t = tid % kTQ, a = tid / kTQ;
+        __syncthreads();   // previous tile fully consumed
+        if (tid <= kTQ) soff[tid] = __ldg(p.offsets + min(base_n + tid, p.N));
+        for (int i = tid; i < HGC * Rpad * kTQP; i += nthr) W[i] = 0.f;
+        for (int i = tid; i < HGC * kTQ * (D / 4); i += nthr) {
+            const int hh = i / (kTQ * (D / 4)), t = (i / (D / 4)) % kTQ, c4 = i % (D / 4);
             const int n = base_n + t;
-            if (n < p.N) {
-                const int start = __ldg(p.offsets + n), end = __ldg(p.offsets + n + 1);
-                float *col = W + a * L * kTQP + t;
-                int i = start;
-                for (; i + 4 <= end; i += 4) {  // 4 independent load chains in flight
-                    int m[4], l[4];
-                    float wv[4];
+            const float4 v = n < p.N ? ld_row4(p.X + ((size_t)n * h + h0 + hh) * D + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4 *>(Xs + (hh * kTQ + t) * XP + 4 * c4) = v;
+        }
+        __syncthreads();
+        const int m0 = soff[0], m1 = soff[kTQ];
+        // ---- histograms of all heads of the group, kPC pairs at a time
+        for (int c0 = m0; c0 < m1; c0 += kPC) {
+            const int cn = min(kPC, m1 - c0);
+            if (c0 > m0) __syncthreads();   // previous chunk consumed
+            for (int i = tid; i < cn; i += nthr) {
+                const int m = PERM ? __ldg(p.pair_id + c0 + i) : c0 + i;
+                const unsigned r0 = clampi(__ldg(p.rel_idx + 3 * (size_t)m + 0), L - 1);
+                const unsigned r1 = clampi(__ldg(p.rel_idx + 3 * (size_t)m + 1), L - 1);
+                const unsigned r2 = clampi(__ldg(p.rel_idx + 3 * (size_t)m + 2), L - 1);
+                pk[i] = r0 | (r1 << 8) | (r2 << 16);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) m[u] = PERM ? __ldg(p.pair_id + i + u) : i + u;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        l[u] = clampi(__ldg(p.rel_idx + 3 * (size_t)m[u] + a), L - 1);
-                        wv[u] = __ldg(p.w + (size_t)m[u] * h + hh);
+                for (int hh = 0; hh < HGC; ++hh) sw[hh * kPC + i] = __ldg(p.w + (size_t)m * h + h0 + hh);
+            }
+            __syncthreads();
+            for (int item = tid; item < HGC * 3 * kTQ; item += nthr) {   // one thread per (head, axis, row)
+                const int t = item % kTQ, a = (item / kTQ) % 3, hh = item / (3 * kTQ);
+                const int s = max(soff[t], c0) - c0, e = min(soff[t + 1], c0 + cn) - c0;
+                float *col = W + hh * Rpad * kTQP + t + (a * L - row_pass_base) * kTQP;
+                const float *wsrc = sw + hh * kPC;
+                const int sh = 8 * a;
+                for (int i = s; i < e; ++i) {
+                    const int bin = (int)((pk[i] >> sh) & 0xffu);
+                    if (MULTI) {   // several passes over the table rows: skip bins outside this pass
+                        const int row = a * L - row_pass_base + bin;
+                        if (row < 0 || row >= Rp) continue;
                     }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) col[l[u] * kTQP] += wv[u];
-                }
-                for (; i < end; ++i) {
-                    const int m = PERM ? __ldg(p.pair_id + i) : i;
-                    const int l = clampi(__ldg(p.rel_idx + 3 * (size_t)m + a), L - 1);
-                    col[l * kTQP] += __ldg(p.w + (size_t)m * h + hh);
+                    col[bin * kTQP] += wsrc[i];
                 }
             }
         }
         __syncthreads();
-#pragma unroll 2
-        for (int t = 0; t < kTQ; t += 4) {
-            const float4 x0 = Xs[(t + 0) * G + cb], x1 = Xs[(t + 1) * G + cb];
-            const float4 x2 = Xs[(t + 2) * G + cb], x3 = Xs[(t + 3) * G + cb];
+        // ---- C += W^T X  (rows of W^T = table rows, k = tile rows, n = channels)
 #pragma unroll
-            for (int k = 0; k < RPT; ++k) {
-                const int row = row_pass_base + lrow + k * NL;
-                if (row < R) {
-                    const float4 wv = *reinterpret_cast<const float4 *>(W + row * kTQP + t);
-                    acc[k] = f4_fma(wv.x, x0, acc[k]);
-                    acc[k] = f4_fma(wv.y, x1, acc[k]);
-                    acc[k] = f4_fma(wv.z, x2, acc[k]);
-                    acc[k] = f4_fma(wv.w, x3, acc[k]);
+        for (int hh = 0; hh < HGC; ++hh) {
+#pragma unroll
+            for (int tp = 0; tp < TPW; ++tp) {
+                const int tile = warp + tp * NW;
+                const int mt = tile / NT, nt = tile % NT;
+                if (mt < n_mt) {
+                    const float *wa = W + (hh * Rpad + mt * 16 + gid) * kTQP + tig;
+                    const float *xb = Xs + (hh * kTQ + tig) * XP + nt * 8 + gid;
+#pragma unroll
+                    for (int k0 = 0; k0 < kTQ; k0 += 8) {
+                        unsigned ah[4], al[4], bh[2], bl[2];
+                        split_tf32(wa[k0], ah[0], al[0]);
+                        split_tf32(wa[8 * kTQP + k0], ah[1], al[1]);
+                        split_tf32(wa[k0 + 4], ah[2], al[2]);
+                        split_tf32(wa[8 * kTQP + k0 + 4], ah[3], al[3]);
+                        split_tf32(xb[k0 * XP], bh[0], bl[0]);
+                        split_tf32(xb[(k0 + 4) * XP], bh[1], bl[1]);
+                        mma_tf32(acc[hh][tp], al, bh);
+                        mma_tf32(acc[hh][tp], ah, bl);
+                        mma_tf32(acc[hh][tp], ah, bh);
+                    }
                 }
             }
         }
     }
 #pragma unroll
-    for (int k = 0; k < RPT; ++k) {
-        const int row = row_pass_base + lrow + k * NL;
-        if (row < R) {
-            const int a = row / L, l = row - a * L;
-            float *dst = p.out + ((size_t)(l * h + hh) * D + 4 * cb) * 3 + a;
-            atomicAdd(dst + 0, acc[k].x);
-            atomicAdd(dst + 3, acc[k].y);
-            atomicAdd(dst + 6, acc[k].z);
-            atomicAdd(dst + 9, acc[k].w);
+    for (int hh = 0; hh < HGC; ++hh)
+#pragma unroll
+        for (int tp = 0; tp < TPW; ++tp) {
+            const int tile = warp + tp * NW;
+            const int mt = tile / NT, nt = tile % NT;
+            if (mt >= n_mt) continue;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int row = row_pass_base + mt * 16 + gid + (c >= 2 ? 8 : 0);
+                if (row >= R) continue;
+                const int a = row / L, l = row - a * L;
+                const int ch = nt * 8 + 2 * tig + (c & 1);
+                atomicAdd(p.out + ((size_t)(l * h + h0 + hh) * D + ch) * 3 + a, acc[hh][tp][c]);
+            }
         }
-    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -364,6 +465,109 @@ __global__ void __launch_bounds__(kThreads) segment_softmax_bwd_kernel(int N, in
                 const size_t o = base + (size_t)i * h;
                 gs[o] = p[o] * (gp[o] - dot);
             }
+        }
+    }
+}
+
+// Head-major variants for h <= 32: lane = (pair slot, head) with HP = next power of two >= h heads per slot, so
+// the 32 lanes read 32/HP consecutive pairs x h heads = one contiguous span of the [M, h] array per step instead of
+// a stride-h walk per head.  Values of the first kSoftCacheHP steps stay in registers.
+constexpr int kSoftCacheHP = 8;
+
+template <int HP>
+__global__ void __launch_bounds__(kThreads) segment_softmax_fwd_hp_kernel(int N, int h, const float *__restrict__ a,
+                                                                          const float *__restrict__ b,
+                                                                          const int *__restrict__ offsets,
+                                                                          float *__restrict__ p) {
+    constexpr int SL = kWarp / HP;
+    const int lane = threadIdx.x % kWarp, hd = lane % HP, slot = lane / HP;
+    const bool on = hd < h;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp, nw = gridDim.x * blockDim.x / kWarp;
+    for (int n = wid; n < N; n += nw) {
+        const int start = __ldg(offsets + n), len = __ldg(offsets + n + 1) - start;
+        if (len <= 0) continue;
+        const size_t base = (size_t)start * h + hd;
+        float v[kSoftCacheHP];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int u = 0; u < kSoftCacheHP; ++u) {
+            const int i = slot + u * SL;
+            v[u] = -INFINITY;
+            if (on && i < len) {
+                v[u] = a[base + (size_t)i * h];
+                if (b) v[u] += b[base + (size_t)i * h];
+            }
+            mx = fmaxf(mx, v[u]);
+        }
+        for (int i = slot + kSoftCacheHP * SL; on && i < len; i += SL) {
+            float s = a[base + (size_t)i * h];
+            if (b) s += b[base + (size_t)i * h];
+            mx = fmaxf(mx, s);
+        }
+#pragma unroll
+        for (int o = HP; o < kWarp; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+#pragma unroll
+        for (int u = 0; u < kSoftCacheHP; ++u) {
+            v[u] = (on && slot + u * SL < len) ? expf(v[u] - mx) : 0.f;
+            sum += v[u];
+        }
+        for (int i = slot + kSoftCacheHP * SL; on && i < len; i += SL) {
+            float s = a[base + (size_t)i * h];
+            if (b) s += b[base + (size_t)i * h];
+            sum += expf(s - mx);
+        }
+#pragma unroll
+        for (int o = HP; o < kWarp; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+#pragma unroll
+        for (int u = 0; u < kSoftCacheHP; ++u) {
+            const int i = slot + u * SL;
+            if (on && i < len) p[base + (size_t)i * h] = v[u] / sum;
+        }
+        for (int i = slot + kSoftCacheHP * SL; on && i < len; i += SL) {
+            float s = a[base + (size_t)i * h];
+            if (b) s += b[base + (size_t)i * h];
+            p[base + (size_t)i * h] = expf(s - mx) / sum;
+        }
+    }
+}
+
+template <int HP>
+__global__ void __launch_bounds__(kThreads) segment_softmax_bwd_hp_kernel(int N, int h, const float *__restrict__ p,
+                                                                          const float *__restrict__ gp,
+                                                                          const int *__restrict__ offsets,
+                                                                          float *__restrict__ gs) {
+    constexpr int SL = kWarp / HP;
+    const int lane = threadIdx.x % kWarp, hd = lane % HP, slot = lane / HP;
+    const bool on = hd < h;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp, nw = gridDim.x * blockDim.x / kWarp;
+    for (int n = wid; n < N; n += nw) {
+        const int start = __ldg(offsets + n), len = __ldg(offsets + n + 1) - start;
+        if (len <= 0) continue;
+        const size_t base = (size_t)start * h + hd;
+        float pv[kSoftCacheHP], gv[kSoftCacheHP];
+        float dot = 0.f;
+#pragma unroll
+        for (int u = 0; u < kSoftCacheHP; ++u) {
+            const int i = slot + u * SL;
+            pv[u] = gv[u] = 0.f;
+            if (on && i < len) {
+                pv[u] = p[base + (size_t)i * h];
+                gv[u] = gp[base + (size_t)i * h];
+            }
+            dot = fmaf(pv[u], gv[u], dot);
+        }
+        for (int i = slot + kSoftCacheHP * SL; on && i < len; i += SL) dot = fmaf(p[base + (size_t)i * h], gp[base + (size_t)i * h], dot);
+#pragma unroll
+        for (int o = HP; o < kWarp; o <<= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+#pragma unroll
+        for (int u = 0; u < kSoftCacheHP; ++u) {
+            const int i = slot + u * SL;
+            if (on && i < len) gs[base + (size_t)i * h] = pv[u] * (gv[u] - dot);
+        }
+        for (int i = slot + kSoftCacheHP * SL; on && i < len; i += SL) {
+            const size_t o = base + (size_t)i * h;
+            gs[o] = p[o] * (gp[o] - dot);
         }
     }
 }
@@ -474,22 +678,34 @@ static int launch_seg_reduce(int D, const SegParams &p, int M, const char *name,
     return launch_seg_reduce_d<32, HAS_Y, HAS_T, PERM>(p, M, name, s);
 }
 
-template <int D, bool PERM>
-static int launch_table_grad_d(const SegParams &p, int M, const char *name, cudaStream_t s) {
-    constexpr int RPT = 4;
-    constexpr int NL = kThreads / (D / 4);
+template <int D, int HGC, bool PERM>
+static int launch_table_grad_hg(const SegParams &p, int M, const char *name, cudaStream_t s) {
     const int R = 3 * p.L;
-    const size_t smem = ((size_t)R * kTQP + kTQ * D) * sizeof(float);
-    auto kern = table_grad_kernel<D, RPT, PERM>;
-    if (int rc = prep_smem(kern, smem)) return rc;
+    const int Rpad = min(256, (R + 15) / 16 * 16);
+    const size_t smem = ((size_t)HGC * Rpad * kTQP + HGC * kTQ * (D + 8) + HGC * kPC + kPC + kTQ + 8) * sizeof(float);
+    auto kern = R <= 256 ? table_grad_kernel<D, HGC, PERM, false> : table_grad_kernel<D, HGC, PERM, true>;
+    if (int rc = prep_smem(table_grad_kernel<D, HGC, PERM, false>, smem)) return rc;
+    if (int rc = prep_smem(table_grad_kernel<D, HGC, PERM, true>, smem)) return rc;
     const int tiles = (p.N + kTQ - 1) / kTQ;
-    const int ctas_per_sm = max(1, min(4, (int)((200 * 1024) / smem)));
-    const int gx = max(1, min(tiles, (kNumSMs * ctas_per_sm + p.h - 1) / p.h));
-    for (int pass = 0; pass < R; pass += NL * RPT) {
+    const int groups = p.h / HGC;
+    const int ctas_per_sm = max(1, min(4, (int)((220 * 1024) / smem)));
+    const int gx = max(1, min(tiles, (kNumSMs * ctas_per_sm + groups - 1) / groups));
+    for (int pass = 0; pass < R; pass += 256) {
         KernelScope ks(name, seg_bytes(p, D, M, true, false, true, false, PERM, 1, false) - 4.0 * p.N * p.h * D, s);
-        kern<<<dim3(gx, p.h), kThreads, smem, s>>>(p, pass);
+        kern<<<dim3(gx, groups), kTGThreads(HGC), smem, s>>>(p, pass, Rpad);
     }
     return check_launch(name);
+}
+
+template <int D, bool PERM>
+static int launch_table_grad_d(const SegParams &p, int M, const char *name, cudaStream_t s) {
+    STB200_REQUIRE(p.L <= 256, STB200_ERR_ARG, "table length %d > 256 not supported by the table-gradient kernel", p.L);
+    constexpr int cap = D == 16 ? 3 : 2;   // heads per CTA: shared-memory histograms and 2*(D/8)*4 accumulators per head
+    switch (largest_head_group(p.h, cap)) {
+        case 3: return launch_table_grad_hg<D, (cap >= 3 ? 3 : 1), PERM>(p, M, name, s);
+        case 2: return launch_table_grad_hg<D, 2, PERM>(p, M, name, s);
+        default: return launch_table_grad_hg<D, 1, PERM>(p, M, name, s);
+    }
 }
 
 template <bool PERM>
@@ -620,7 +836,14 @@ int stb200_segment_softmax_forward(int N, int M, int h, const float *a, const fl
     const int blocks = max(1, min((N + kThreads / kWarp - 1) / (kThreads / kWarp), kNumSMs * 8));
     {
         KernelScope ks("segment_softmax_fwd", 4.0 * M * h * (b ? 3 : 2) + 4.0 * (N + 1), (cudaStream_t)stream);
-        segment_softmax_fwd_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(N, h, a, b, index0_offsets, p);
+        cudaStream_t s = (cudaStream_t)stream;
+        if (h <= 1) segment_softmax_fwd_hp_kernel<1><<<blocks, kThreads, 0, s>>>(N, h, a, b, index0_offsets, p);
+        else if (h <= 2) segment_softmax_fwd_hp_kernel<2><<<blocks, kThreads, 0, s>>>(N, h, a, b, index0_offsets, p);
+        else if (h <= 4) segment_softmax_fwd_hp_kernel<4><<<blocks, kThreads, 0, s>>>(N, h, a, b, index0_offsets, p);
+        else if (h <= 8) segment_softmax_fwd_hp_kernel<8><<<blocks, kThreads, 0, s>>>(N, h, a, b, index0_offsets, p);
+        else if (h <= 16) segment_softmax_fwd_hp_kernel<16><<<blocks, kThreads, 0, s>>>(N, h, a, b, index0_offsets, p);
+        else if (h <= 32) segment_softmax_fwd_hp_kernel<32><<<blocks, kThreads, 0, s>>>(N, h, a, b, index0_offsets, p);
+        else segment_softmax_fwd_kernel<<<blocks, kThreads, 0, s>>>(N, h, a, b, index0_offsets, p);
     }
     return check_launch("segment_softmax_fwd");
 }
@@ -633,7 +856,14 @@ int stb200_segment_softmax_backward(int N, int M, int h, const float *p, const f
     const int blocks = max(1, min((N + kThreads / kWarp - 1) / (kThreads / kWarp), kNumSMs * 8));
     {
         KernelScope ks("segment_softmax_bwd", 4.0 * M * h * 3 + 4.0 * (N + 1), (cudaStream_t)stream);
-        segment_softmax_bwd_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(N, h, p, grad_p, index0_offsets, grad_s);
+        cudaStream_t s = (cudaStream_t)stream;
+        if (h <= 1) segment_softmax_bwd_hp_kernel<1><<<blocks, kThreads, 0, s>>>(N, h, p, grad_p, index0_offsets, grad_s);
+        else if (h <= 2) segment_softmax_bwd_hp_kernel<2><<<blocks, kThreads, 0, s>>>(N, h, p, grad_p, index0_offsets, grad_s);
+        else if (h <= 4) segment_softmax_bwd_hp_kernel<4><<<blocks, kThreads, 0, s>>>(N, h, p, grad_p, index0_offsets, grad_s);
+        else if (h <= 8) segment_softmax_bwd_hp_kernel<8><<<blocks, kThreads, 0, s>>>(N, h, p, grad_p, index0_offsets, grad_s);
+        else if (h <= 16) segment_softmax_bwd_hp_kernel<16><<<blocks, kThreads, 0, s>>>(N, h, p, grad_p, index0_offsets, grad_s);
+        else if (h <= 32) segment_softmax_bwd_hp_kernel<32><<<blocks, kThreads, 0, s>>>(N, h, p, grad_p, index0_offsets, grad_s);
+        else segment_softmax_bwd_kernel<<<blocks, kThreads, 0, s>>>(N, h, p, grad_p, index0_offsets, grad_s);
     }
     return check_launch("segment_softmax_bwd");
 }

@@ -364,6 +364,11 @@ extern "C" int stb200_furthestsampling(int b, int n, const float *xyz, const int
     int cs = 1;
     while (cs < env_int("STB200_FPS_CLUSTER", kMaxCluster) && b * cs * 2 <= kNumSMs && cs * threads * per_thread < n) cs <<= 1;
     for (; cs >= 1; cs >>= 1) {
+        // A thread's points are i = gtid + u * (cs * threads); "first strict maximum inside the thread" equals the
+        // reference's tie order only if they all share i mod B, i.e. cs * threads must be a multiple of B.
+        int threads_cs = threads;
+        while (cs * threads_cs < (1 << logB) && threads_cs < 1024) threads_cs <<= 1;
+        const int threads = threads_cs;
         const int need = (n + cs * threads - 1) / (cs * threads);
         int rc = STB200_ERR_ARG;
         if (need <= 1) rc = launch_fps<1>(b, cs, threads, xyz, offset, new_offset, idx, logB, s);

@@ -47,6 +47,22 @@ def test_fps_exact_vs_oracle_and_reference(sizes, ds, lattice):
         assert np.array_equal(ref, want), "oracle disagrees with the reference kernel"
 
 
+@pytest.mark.parametrize("n,spacing", [(700, 0.5), (1251, 0.25), (4000, 0.25), (5001, 0.5), (20001, 0.25)])
+def test_fps_exact_with_massive_ties(n, spacing):
+    """Coarse lattice: most distances tie exactly, so every level of the (distance, rank) reduction and the in-thread
+    scan order are exercised for each launch configuration (single CTA, small / large clusters)."""
+    rng = np.random.default_rng(n)
+    xyz = (np.round(rng.uniform(0, 6, (n, 3)) / spacing) * spacing).astype(np.float32)
+    offset = np.array([n], np.int32)
+    new_offset = io.fps_new_offset(offset, 8)
+    want = fps_oracle.furthestsampling(xyz, offset, new_offset)
+    assert np.array_equal(ours(xyz, offset, new_offset), want)
+    two = np.concatenate([xyz, xyz[::-1].copy()])
+    offset2 = np.array([n, 2 * n], np.int32)
+    new_offset2 = io.fps_new_offset(offset2, 4)
+    assert np.array_equal(ours(two, offset2, new_offset2), fps_oracle.furthestsampling(two, offset2, new_offset2))
+
+
 def test_fps_full_size_scene():
     """BASELINE cfg2 scene size: 80k points, 10 001 samples; oracle takes ~2 s."""
     from stratified_transformer_b200.synthetic import make_scene

@@ -1,7 +1,7 @@
 """ctypes binding of libstb200.so (the C ABI declared in include/stb200.h).
 
 There is deliberately NO fallback: if the shared library is missing or a call fails, this raises.
-Nothing here imports `oracle/`.
+Nothing in this package imports the CPU checker that lives outside it.
 """
 from __future__ import annotations
 

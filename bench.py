@@ -5,8 +5,8 @@ Workload (BASELINE.json configs[1], restricted to the hot path of SURVEY §8): p
 scenes; the S3DIS layer schedule of config/s3dis/s3dis_stratified_transformer.yaml (channels 48/96/192/384,
 heads 3/6/12/24, depths 2/2/6/2, window 0.16*2^l, quant 0.01*2^l, downsample_scale 8, point hierarchy
 n -> int(n*0.25)+1 per TransitionDown).  One step = for every layer: FPS of the stratified keys + pair-index
-construction for both block parities (+ rel-pos index), then for every block: attention_step1 ->
-dot_prod_with_idx -> segment softmax -> attention_step2_with_rel_pos_value forward and the full backward
+construction for both block parities (+ rel-pos index), then for every block: attention_step1 +
+dot_prod_with_idx (one fused pass) -> segment softmax -> attention_step2_with_rel_pos_value forward and the full backward
 (grads of q, k, v and the three tables).  The dense GEMMs around the path (qkv/proj Linear, MLP, KPConv) and
 TransitionDown/Upsample are out of scope; the point hierarchy is precomputed data.
 
@@ -221,36 +221,41 @@ def build_inputs(a, rank, dev):
 
 
 def device_step(levels, grads_out):
-    """One pass of the hot path with device-resident operands through the extension-level API."""
-    from stratified_transformer_b200 import index, pointops2_cuda as ext
+    """One pass of the hot path with device-resident operands through the extension-level API (fused entry points:
+    logits = q.k + rel-pos bias in one pass, segment softmax, aggregation; and their single-pass gradients)."""
+    import ctypes
+    from stratified_transformer_b200 import _cabi, index, pointops2_cuda as ext
+    stream = torch.cuda.current_stream().cuda_stream
     for lv in levels:
         cfg = lv["cfg"]
-        h, C, L = cfg["h"], cfg["C"], lv["L"]
+        h, L = cfg["h"], lv["L"]
         li = index.build_layer_index(lv["xyz"], lv["offset"], cfg["window"], cfg["quant"], DS_SCALE)
         q, k, v, g = lv["q"], lv["k"], lv["v"], lv["g"]
         N = q.shape[0]
         dev = q.device
         for blk in range(cfg["depth"]):
             pi = li.for_block(blk)
-            M, off, i1, rel = pi.M, pi.index_0_offsets, pi.index_1, pi.rel_idx
+            M, off = pi.M, pi.index_0_offsets
             tq, tk, tv = lv["tables"][blk]
-            attn = torch.empty(M, h, device=dev); bias = torch.empty(M, h, device=dev); p = torch.empty(M, h, device=dev)
+            ix = pi.c_struct(L, backward=True)
+            s = torch.empty(M, h, device=dev); p = torch.empty(M, h, device=dev)
             out = torch.empty(N, h, HEAD_DIM, device=dev)
-            ext.attention_step1_forward_cuda_v2(N, M, h, C, 0, q, k, off, i1, attn)
-            ext.dot_prod_with_idx_forward_cuda_v3(N, M, h, HEAD_DIM, 0, q, off, k, i1, tq, tk, rel, bias)
-            ext.segment_softmax_forward_cuda(N, M, h, attn, bias, off, p)
-            ext.attention_step2_with_rel_pos_value_forward_cuda_v2(N, M, h, HEAD_DIM, 0, p, v, off, i1, tv, rel, out)
+            _cabi.call("stb200_window_logits_forward", ctypes.byref(ix), h, HEAD_DIM, L, q.data_ptr(), k.data_ptr(),
+                       tq.data_ptr(), tk.data_ptr(), s.data_ptr(), stream)
+            ext.segment_softmax_forward_cuda(N, M, h, s, None, off, p)
+            _cabi.call("stb200_window_aggregate_forward", ctypes.byref(ix), h, HEAD_DIM, L, p.data_ptr(), v.data_ptr(),
+                       tv.data_ptr(), out.data_ptr(), stream)
             # backward
-            tc = pi.tcsr
-            gp = attn; gs = bias                       # reuse the M-sized buffers
+            gp = s                                      # reuse the M-sized buffer
             gv = torch.zeros_like(v); gtv = torch.zeros_like(tv)
-            ext.attention_step2_with_rel_pos_value_backward_cuda_v2(N, M, h, HEAD_DIM, 0, g, off, i1, p, v, tv, rel, gp, gv, gtv, tc)
+            _cabi.call("stb200_window_aggregate_backward", ctypes.byref(ix), h, HEAD_DIM, L, g.data_ptr(), p.data_ptr(),
+                       v.data_ptr(), tv.data_ptr(), gp.data_ptr(), gv.data_ptr(), gtv.data_ptr(), stream)
+            gs = torch.empty(M, h, device=dev)
             ext.segment_softmax_backward_cuda(N, M, h, p, gp, off, gs)
-            gq2 = torch.empty_like(q); gk2 = torch.zeros_like(k); gtq = torch.zeros_like(tq); gtk = torch.zeros_like(tk)
-            ext.dot_prod_with_idx_backward_cuda_v3(N, M, h, HEAD_DIM, 0, gs, q, off, k, i1, tq, tk, rel, gq2, gk2, gtq, gtk, tc)
-            gq = torch.empty_like(q)
-            ext.attention_step1_backward_cuda_v2(N, M, h, C, 0, gs, off, i1, q, k, gq, gk2, tc)   # grad_k accumulates
-            gq.add_(gq2)
+            gq = torch.empty_like(q); gk = torch.zeros_like(k); gtq = torch.zeros_like(tq); gtk = torch.zeros_like(tk)
+            _cabi.call("stb200_window_logits_backward", ctypes.byref(ix), h, HEAD_DIM, L, gs.data_ptr(), q.data_ptr(),
+                       k.data_ptr(), tq.data_ptr(), tk.data_ptr(), gq.data_ptr(), gk.data_ptr(), gtq.data_ptr(),
+                       gtk.data_ptr(), stream)
             grads_out.append((gtq, gtk, gtv))
     return grads_out
 

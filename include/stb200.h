@@ -182,6 +182,38 @@ int stb200_rel_pos_index_swin(int N, const float *xyz, const int *index0_offsets
                               float window_size, float quant_size, float shift_size, int quant_grid_length,
                               float *xq_scratch, unsigned *mm_scratch, int *rel_idx, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused entry points (new; no reference counterpart).  The reference's WindowAttention issues attention_step1_v2 and
+ * dot_prod_with_idx_v3 back to back on the same pairs (model/stratified_transformer.py:183,194) and adds the results
+ * (:203); both gather the same key rows.  stb200_window_logits_* does q.k + rel-pos bias in one pass (and the matching
+ * single-pass gradients); stb200_window_aggregate_* is attention_step2_with_rel_pos_value_v2 driven by the same index
+ * descriptor.  rel_packed / t_rel_packed (optional, stb200_pack_rel) replace the 12-byte rel_idx rows by one 32-bit
+ * word per pair (three 10-bit bins) in query-segment / key-segment order. */
+typedef struct stb200_index {
+    int N, M;
+    const int *index0_offsets; /* [N+1] */
+    const int *index1;         /* [M]   */
+    const int *rel_idx;        /* [M,3] (may be NULL when rel_packed is given and no transposed kernel needs it) */
+    const int *t_offsets;      /* [N+1] transposed CSR, backward only */
+    const int *t_pair;         /* [M]   */
+    const int *t_index0;       /* [M]   */
+    const unsigned *rel_packed;   /* [M] optional */
+    const unsigned *t_rel_packed; /* [M] optional, bins of pair t_pair[t] */
+} stb200_index;
+
+/* out[i] = r0 | r1 << 10 | r2 << 20 of pair (perm ? perm[i] : i), bins clamped to [0, L) */
+int stb200_pack_rel(int M, int L, const int *rel_idx, const int *perm, unsigned *out, void *stream);
+int stb200_window_logits_forward(const stb200_index *ix, int h, int hdim, int L, const float *q, const float *k,
+                                 const float *table_q, const float *table_k, float *logits, void *stream);
+int stb200_window_logits_backward(const stb200_index *ix, int h, int hdim, int L, const float *grad_logits,
+                                  const float *q, const float *k, const float *table_q, const float *table_k,
+                                  float *grad_q, float *grad_k, float *grad_table_q, float *grad_table_k, void *stream);
+int stb200_window_aggregate_forward(const stb200_index *ix, int h, int hdim, int L, const float *attn, const float *v,
+                                    const float *table_v, float *output, void *stream);
+int stb200_window_aggregate_backward(const stb200_index *ix, int h, int hdim, int L, const float *grad_out,
+                                     const float *attn, const float *v, const float *table_v, float *grad_attn,
+                                     float *grad_v, float *grad_table_v, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

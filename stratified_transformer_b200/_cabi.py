@@ -14,6 +14,15 @@ LIB_PATH = os.path.join(_HERE, "lib", "libstb200.so")
 _c_int, _c_uint, _c_void_p, _c_size_t = ctypes.c_int, ctypes.c_uint, ctypes.c_void_p, ctypes.c_size_t
 P = _c_void_p
 
+class IndexStruct(ctypes.Structure):
+    """mirror of `stb200_index` (include/stb200.h)"""
+    _fields_ = [("N", ctypes.c_int), ("M", ctypes.c_int), ("index0_offsets", ctypes.c_void_p), ("index1", ctypes.c_void_p),
+                ("rel_idx", ctypes.c_void_p), ("t_offsets", ctypes.c_void_p), ("t_pair", ctypes.c_void_p),
+                ("t_index0", ctypes.c_void_p), ("rel_packed", ctypes.c_void_p), ("t_rel_packed", ctypes.c_void_p)]
+
+
+_IX = ctypes.POINTER(IndexStruct)
+
 # name -> argtypes (every function returns int unless listed in _RESTYPES)
 _SIGNATURES = {
     "stb200_transpose_csr": [_c_int, _c_int, P, P, P, P, P, P, _c_size_t, P],
@@ -37,6 +46,11 @@ _SIGNATURES = {
     "stb200_stratified_pairs_count": [_c_int, _c_int, P, P, ctypes.c_float, _c_int, P, _c_int, P, _c_size_t, P, P, P],
     "stb200_stratified_pairs_fill": [_c_int, P, ctypes.c_float, ctypes.c_float, _c_int, P, _c_size_t, P, P, P, P, _c_int, P],
     "stb200_rel_pos_index_stratified": [_c_int, P, P, P, ctypes.c_float, ctypes.c_float, P, P],
+    "stb200_pack_rel": [_c_int, _c_int, P, P, P, P],
+    "stb200_window_logits_forward": [_IX, _c_int, _c_int, _c_int] + [P] * 6,
+    "stb200_window_logits_backward": [_IX, _c_int, _c_int, _c_int] + [P] * 10,
+    "stb200_window_aggregate_forward": [_IX, _c_int, _c_int, _c_int] + [P] * 5,
+    "stb200_window_aggregate_backward": [_IX, _c_int, _c_int, _c_int] + [P] * 8,
     "stb200_rel_pos_index_swin": [_c_int, P, P, P, ctypes.c_float, ctypes.c_float, ctypes.c_float, _c_int, P, P, P, P],
 }
 _RESTYPES = {

@@ -39,6 +39,7 @@ struct SegParams {
     const int *pair_id;    // pair id per segment slot (transposed CSR) or null
     const float *Tx, *Ty;  // rel-pos tables [L, h, D, 3]
     const int *rel_idx;    // [M, 3]
+    const unsigned *packed; // optional: the three bins of each segment slot packed 10 bits each (replaces rel_idx)
     float *out;
     int accumulate;
 };
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(kThreads) seg_dot_kernel(const SegParams p) {
                 const int mt = start + c0 + min(lane, cnt - 1);
                 const int j_l = ld_stream(p.gather_idx + mt);
                 unsigned pk_l = 0;
-                if (EX || EY) pk_l = pack_bins(p.rel_idx + 3 * (size_t)mt, L);
+                if (EX || EY) pk_l = p.packed ? __ldg(p.packed + mt) : pack_bins(p.rel_idx + 3 * (size_t)mt, L);
                 const int items = cnt * HG;
                 for (int e0 = 0; e0 < items; e0 += NS * kUnroll) {
                     float4 y4[kUnroll];
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(kThreads) seg_reduce_kernel(const SegParams p)
                 const int m_l = PERM ? ld_stream(p.pair_id + tl) : tl;
                 const int j_l = HAS_Y ? ld_stream(p.gather_idx + tl) : 0;
                 unsigned pk_l = 0;
-                if (HAS_T) pk_l = pack_bins(p.rel_idx + 3 * (size_t)m_l, L);
+                if (HAS_T) pk_l = p.packed ? __ldg(p.packed + tl) : pack_bins(p.rel_idx + 3 * (size_t)m_l, L);
                 constexpr int U = 2;   // pair slots per lane group in flight (U * HG row gathers)
                 for (int s0 = 0; s0 < cnt; s0 += NS * U) {
                     float4 val[U][HG];
@@ -318,10 +319,15 @@ __global__ void __launch_bounds__(kTGThreads(HGC), (D == 16 ? 2 : 1)) table_grad
             if (c0 > m0) __syncthreads();   // previous chunk consumed
             for (int i = tid; i < cn; i += nthr) {
                 const int m = PERM ? __ldg(p.pair_id + c0 + i) : c0 + i;
-                const unsigned r0 = clampi(__ldg(p.rel_idx + 3 * (size_t)m + 0), L - 1);
-                const unsigned r1 = clampi(__ldg(p.rel_idx + 3 * (size_t)m + 1), L - 1);
-                const unsigned r2 = clampi(__ldg(p.rel_idx + 3 * (size_t)m + 2), L - 1);
-                pk[i] = r0 | (r1 << 8) | (r2 << 16);
+                if (p.packed) {
+                    const unsigned q = __ldg(p.packed + c0 + i);   // 10-bit fields -> 8-bit fields
+                    pk[i] = (q & 0xffu) | (((q >> 10) & 0xffu) << 8) | (((q >> 20) & 0xffu) << 16);
+                } else {
+                    const unsigned r0 = clampi(__ldg(p.rel_idx + 3 * (size_t)m + 0), L - 1);
+                    const unsigned r1 = clampi(__ldg(p.rel_idx + 3 * (size_t)m + 1), L - 1);
+                    const unsigned r2 = clampi(__ldg(p.rel_idx + 3 * (size_t)m + 2), L - 1);
+                    pk[i] = r0 | (r1 << 8) | (r2 << 16);
+                }
 #pragma unroll
                 for (int hh = 0; hh < HGC; ++hh) sw[hh * kPC + i] = __ldg(p.w + (size_t)m * h + h0 + hh);
             }
@@ -866,6 +872,86 @@ int stb200_segment_softmax_backward(int N, int M, int h, const float *p, const f
         else segment_softmax_bwd_kernel<<<blocks, kThreads, 0, s>>>(N, h, p, grad_p, index0_offsets, grad_s);
     }
     return check_launch("segment_softmax_bwd");
+}
+
+// ---- fused entry points (new; see include/stb200.h): logits = q.k + rel-pos bias in one pass over the pairs,
+// and the same aggregation / gradient kernels driven by an stb200_index (optionally with pre-packed bins).
+static int check_index(const stb200_index *ix, bool need_t) {
+    STB200_REQUIRE(ix && ix->N >= 0 && ix->M >= 0 && ix->index0_offsets, STB200_ERR_ARG, "bad stb200_index");
+    STB200_REQUIRE(ix->M == 0 || (ix->index1 && (ix->rel_idx || ix->rel_packed)), STB200_ERR_ARG, "stb200_index: index1 / rel_idx missing");
+    if (need_t) {
+        STB200_REQUIRE(ix->t_offsets && ix->t_pair && ix->t_index0, STB200_ERR_ARG, "transposed CSR required (stb200_transpose_csr)");
+        STB200_REQUIRE(ix->rel_idx || (ix->rel_packed && ix->t_rel_packed), STB200_ERR_ARG, "stb200_index: rel_idx or both packed arrays required");
+    }
+    return STB200_OK;
+}
+
+int stb200_window_logits_forward(const stb200_index *ix, int h, int hdim, int L, const float *q, const float *k,
+                                 const float *table_q, const float *table_k, float *logits, void *stream) {
+    if (int rc = check_index(ix, false)) return rc;
+    if (int rc = check_dims(ix->N, ix->M, h, hdim)) return rc;
+    if (ix->M == 0) return STB200_OK;
+    STB200_REQUIRE(L > 0 && L <= 1024 && q && k && table_q && table_k && logits, STB200_ERR_ARG, "null pointer or bad L");
+    SegParams p{};
+    p.N = ix->N; p.h = h; p.L = L; p.X = q; p.Y = k; p.offsets = ix->index0_offsets; p.gather_idx = ix->index1;
+    p.Tx = table_q; p.Ty = table_k; p.rel_idx = ix->rel_idx; p.packed = ix->rel_packed; p.out = logits;
+    return launch_seg_dot<true, true, true>(hdim, p, ix->M, "seg_dot[logits_fwd]", (cudaStream_t)stream);
+}
+
+int stb200_window_logits_backward(const stb200_index *ix, int h, int hdim, int L, const float *grad_logits,
+                                  const float *q, const float *k, const float *table_q, const float *table_k,
+                                  float *grad_q, float *grad_k, float *grad_table_q, float *grad_table_k, void *stream) {
+    if (int rc = check_index(ix, true)) return rc;
+    if (int rc = check_dims(ix->N, ix->M, h, hdim)) return rc;
+    STB200_REQUIRE(L > 0 && L <= 256 && grad_logits && q && k && table_q && table_k && grad_q && grad_k && grad_table_q &&
+                       grad_table_k, STB200_ERR_ARG, "null pointer or bad L");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int M = ix->M;
+    SegParams p{};
+    p.N = ix->N; p.h = h; p.L = L; p.w = grad_logits; p.rel_idx = ix->rel_idx;
+    // grad_q = sum g * (k[i1] + Eq)                                              (overwritten)
+    p.packed = ix->rel_packed; p.offsets = ix->index0_offsets; p.gather_idx = ix->index1; p.Y = k; p.Tx = table_q; p.out = grad_q;
+    if (int rc = launch_seg_reduce<true, true, false>(hdim, p, M, "seg_reduce[logits_bwd_gq]", s)) return rc;
+    p.X = q; p.out = grad_table_q;
+    if (int rc = launch_table_grad<false>(hdim, p, M, "table_grad[logits_bwd_gtq]", s)) return rc;
+    // grad_k += sum over incoming pairs g * (q[i0] + Ek)                          (accumulated)
+    p.packed = ix->t_rel_packed; p.offsets = ix->t_offsets; p.pair_id = ix->t_pair; p.gather_idx = ix->t_index0;
+    p.Y = q; p.Tx = table_k; p.out = grad_k; p.accumulate = 1;
+    if (int rc = launch_seg_reduce<true, true, true>(hdim, p, M, "seg_reduce_t[logits_bwd_gk]", s)) return rc;
+    p.X = k; p.out = grad_table_k;
+    return launch_table_grad<true>(hdim, p, M, "table_grad_t[logits_bwd_gtk]", s);
+}
+
+int stb200_window_aggregate_forward(const stb200_index *ix, int h, int hdim, int L, const float *attn, const float *v,
+                                    const float *table_v, float *output, void *stream) {
+    if (int rc = check_index(ix, false)) return rc;
+    if (int rc = check_dims(ix->N, ix->M, h, hdim)) return rc;
+    STB200_REQUIRE(L > 0 && L <= 1024 && output && (ix->M == 0 || (attn && v && table_v)), STB200_ERR_ARG, "null pointer or bad L");
+    SegParams p{};
+    p.N = ix->N; p.h = h; p.L = L; p.w = attn; p.Y = v; p.offsets = ix->index0_offsets; p.gather_idx = ix->index1;
+    p.Tx = table_v; p.rel_idx = ix->rel_idx; p.packed = ix->rel_packed; p.out = output;
+    return launch_seg_reduce<true, true, false>(hdim, p, ix->M, "seg_reduce[aggregate_fwd]", (cudaStream_t)stream);
+}
+
+int stb200_window_aggregate_backward(const stb200_index *ix, int h, int hdim, int L, const float *grad_out,
+                                     const float *attn, const float *v, const float *table_v, float *grad_attn,
+                                     float *grad_v, float *grad_table_v, void *stream) {
+    if (int rc = check_index(ix, true)) return rc;
+    if (int rc = check_dims(ix->N, ix->M, h, hdim)) return rc;
+    STB200_REQUIRE(L > 0 && L <= 256 && grad_out && attn && v && table_v && grad_attn && grad_v && grad_table_v, STB200_ERR_ARG,
+                   "null pointer or bad L");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int M = ix->M;
+    SegParams p{};
+    p.N = ix->N; p.h = h; p.L = L; p.rel_idx = ix->rel_idx; p.packed = ix->rel_packed;
+    p.X = grad_out; p.Y = v; p.offsets = ix->index0_offsets; p.gather_idx = ix->index1; p.Tx = table_v; p.out = grad_attn;
+    if (M > 0)
+        if (int rc = launch_seg_dot<true, true, false>(hdim, p, M, "seg_dot[aggregate_bwd_gattn]", s)) return rc;
+    p.w = attn; p.out = grad_table_v;
+    if (int rc = launch_table_grad<false>(hdim, p, M, "table_grad[aggregate_bwd_gtv]", s)) return rc;
+    p.packed = nullptr; p.Y = grad_out; p.offsets = ix->t_offsets; p.pair_id = ix->t_pair; p.gather_idx = ix->t_index0;
+    p.out = grad_v; p.accumulate = 1;
+    return launch_seg_reduce<true, false, true>(hdim, p, M, "seg_reduce_t[aggregate_bwd_gv]", s);
 }
 
 }  // extern "C"

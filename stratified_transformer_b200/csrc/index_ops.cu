@@ -39,6 +39,16 @@ __global__ void gather_int_kernel(int M, const int *__restrict__ src, const int 
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) dst[i] = __ldg(src + __ldg(idx + i));
 }
 
+__global__ void pack_rel_kernel(int M, int L, const int *__restrict__ rel_idx, const int *__restrict__ perm,
+                                unsigned *__restrict__ out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
+        const size_t m = perm ? __ldg(perm + i) : i;
+        const unsigned r0 = min(max(__ldg(rel_idx + 3 * m + 0), 0), L - 1), r1 = min(max(__ldg(rel_idx + 3 * m + 1), 0), L - 1),
+                       r2 = min(max(__ldg(rel_idx + 3 * m + 2), 0), L - 1);
+        out[i] = r0 | (r1 << 10) | (r2 << 20);
+    }
+}
+
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 static int key_bits(int N) {
@@ -59,6 +69,17 @@ static size_t sort_temp_bytes(int N, int M) {
 using namespace stb200;
 
 extern "C" {
+
+int stb200_pack_rel(int M, int L, const int *rel_idx, const int *perm, unsigned *out, void *stream) {
+    STB200_REQUIRE(M >= 0 && L > 0 && L <= 1024, STB200_ERR_ARG, "bad M / L (L <= 1024)");
+    if (M == 0) return STB200_OK;
+    STB200_REQUIRE(rel_idx && out, STB200_ERR_ARG, "null pointer");
+    {
+        KernelScope ks("pack_rel", 16.0 * M + (perm ? 4.0 * M : 0.0), (cudaStream_t)stream);
+        pack_rel_kernel<<<max(1, min((M + 255) / 256, kNumSMs * 8)), 256, 0, (cudaStream_t)stream>>>(M, L, rel_idx, perm, out);
+    }
+    return check_launch("pack_rel");
+}
 
 size_t stb200_transpose_csr_workspace_bytes(int N, int M) {
     if (M <= 0) return 256;

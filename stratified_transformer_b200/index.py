@@ -32,6 +32,7 @@ class PairIndex:
     M: int
     index_0: torch.Tensor | None = None    # [M]   only when asked for (v1 ops, scatter_softmax callers)
     _tcsr: ext.TransposedCSR | None = field(default=None, repr=False)
+    _packed: dict = field(default_factory=dict, repr=False)   # L -> (rel_packed, t_rel_packed | None)
 
     @property
     def N(self) -> int:
@@ -43,6 +44,28 @@ class PairIndex:
         if self._tcsr is None:
             self._tcsr = ext.build_transposed_csr(self.index_0_offsets, self.index_1)
         return self._tcsr
+
+    def _pack(self, L: int, perm):
+        out = torch.empty(self.M, dtype=torch.int32, device=self.index_1.device)
+        _cabi.call("stb200_pack_rel", self.M, int(L), self.rel_idx.data_ptr(), None if perm is None else perm.data_ptr(),
+                   out.data_ptr(), _stream())
+        return out
+
+    def c_struct(self, L: int, backward: bool = False) -> "_cabi.IndexStruct":
+        """`stb200_index` for the fused entry points; packs the rel-pos bins on first use (per table length)."""
+        ent = self._packed.get(L)
+        if ent is None:
+            ent = [self._pack(L, None), None]
+            self._packed[L] = ent
+        if backward and ent[1] is None:
+            ent[1] = self._pack(L, self.tcsr.t_pair)
+        st = _cabi.IndexStruct(self.N, self.M, self.index_0_offsets.data_ptr(), self.index_1.data_ptr(),
+                               self.rel_idx.data_ptr(), None, None, None, ent[0].data_ptr(), None)
+        if backward:
+            t = self.tcsr
+            st.t_offsets, st.t_pair, st.t_index0 = t.t_offsets.data_ptr(), t.t_pair.data_ptr(), t.t_index0.data_ptr()
+            st.t_rel_packed = ent[1].data_ptr()
+        return st
 
 
 def fps_new_offset(offset: torch.Tensor, downsample_scale: int) -> torch.Tensor:

@@ -20,9 +20,12 @@ shape depends on it); the ops run on torch's current stream; inputs are pinned t
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 from torch.autograd import Function
 
+from . import _cabi
 from . import pointops2_cuda as pointops_cuda
 
 
@@ -185,6 +188,77 @@ class SegmentSoftmax(Function):
         pointops_cuda.segment_softmax_backward_cuda(index0_offsets.shape[0] - 1, M, h, p, grad_p.contiguous(),
                                                     index0_offsets, grad_s)
         return grad_s, (grad_s if ctx.has_b else None), None
+
+
+class WindowLogits(Function):
+    """logits[m,h] = <q[i0],k[i1]> + <q[i0],Eq(m)> + <k[i1],Ek(m)> in one pass over the pairs: the fused form of
+    attention_step1_v2 + dot_prod_with_idx_v3 + add (model/stratified_transformer.py:183-203).  `pair_index` is a
+    stratified_transformer_b200.index.PairIndex."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, q, k, table_q, table_k, pair_index):
+        _contig(q, k, table_q, table_k)
+        N, h, d = q.shape
+        L = table_q.shape[0]
+        out = torch.empty(pair_index.M, h, dtype=torch.float32, device=q.device)
+        _cabi.call("stb200_window_logits_forward", ctypes.byref(pair_index.c_struct(L)), h, d, L, q.data_ptr(), k.data_ptr(),
+                   table_q.data_ptr(), table_k.data_ptr(), out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        ctx.save_for_backward(q, k, table_q, table_k)
+        ctx.pair_index = pair_index
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, grad_out):
+        q, k, table_q, table_k = ctx.saved_tensors
+        N, h, d = q.shape
+        L = table_q.shape[0]
+        grad_out = grad_out.contiguous()
+        gq, gk = torch.empty_like(q), torch.zeros_like(k)
+        gtq, gtk = torch.zeros_like(table_q), torch.zeros_like(table_k)
+        _cabi.call("stb200_window_logits_backward", ctypes.byref(ctx.pair_index.c_struct(L, backward=True)), h, d, L,
+                   grad_out.data_ptr(), q.data_ptr(), k.data_ptr(), table_q.data_ptr(), table_k.data_ptr(), gq.data_ptr(),
+                   gk.data_ptr(), gtq.data_ptr(), gtk.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        return gq, gk, gtq, gtk, None
+
+
+def window_logits(q, k, table_q, table_k, pair_index):
+    return WindowLogits.apply(q, k, table_q, table_k, pair_index)
+
+
+class WindowAggregate(Function):
+    """attention_step2_with_rel_pos_value_v2 driven by a PairIndex (packed rel-pos bins, shared transposed CSR)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, attn, v, table_v, pair_index):
+        _contig(attn, v, table_v)
+        N, h, d = v.shape
+        L = table_v.shape[0]
+        out = torch.empty(N, h, d, dtype=torch.float32, device=v.device)
+        _cabi.call("stb200_window_aggregate_forward", ctypes.byref(pair_index.c_struct(L)), h, d, L, attn.data_ptr(),
+                   v.data_ptr(), table_v.data_ptr(), out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        ctx.save_for_backward(attn, v, table_v)
+        ctx.pair_index = pair_index
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, grad_out):
+        attn, v, table_v = ctx.saved_tensors
+        N, h, d = v.shape
+        L = table_v.shape[0]
+        grad_out = grad_out.contiguous()
+        ga, gv, gt = torch.empty_like(attn), torch.zeros_like(v), torch.zeros_like(table_v)
+        _cabi.call("stb200_window_aggregate_backward", ctypes.byref(ctx.pair_index.c_struct(L, backward=True)), h, d, L,
+                   grad_out.data_ptr(), attn.data_ptr(), v.data_ptr(), table_v.data_ptr(), ga.data_ptr(), gv.data_ptr(),
+                   gt.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        return ga, gv, gt, None
+
+
+def window_aggregate(attn, v, table_v, pair_index):
+    return WindowAggregate.apply(attn, v, table_v, pair_index)
 
 
 def segment_softmax(a, index0_offsets, b=None):

@@ -66,9 +66,16 @@ class WindowAttention(nn.Module):
         query, key, value = qkv[0], qkv[1], qkv[2]
         query = query * self.scale
         off, i1, rel = idx.index_0_offsets, idx.index_1, idx.rel_idx
-        attn_flat = pointops.attention_step1_v2(query.float(), key.float(), i1, off, idx.n_max)
         bias = None
-        if self.rel_query and self.rel_key:
+        fused = self.rel_query and self.rel_key
+        if fused:   # q.k + rel-pos bias in one pass over the pairs
+            attn_flat = pointops.window_logits(query.float(), key.float(), self.relative_pos_query_table.float(),
+                                               self.relative_pos_key_table.float(), idx)
+        else:
+            attn_flat = pointops.attention_step1_v2(query.float(), key.float(), i1, off, idx.n_max)
+        if fused:
+            pass
+        elif self.rel_query and self.rel_key:
             bias = pointops.dot_prod_with_idx_v3(query.float(), off, idx.n_max, key.float(), i1,
                                                  self.relative_pos_query_table.float(),
                                                  self.relative_pos_key_table.float(), rel)
@@ -82,8 +89,7 @@ class WindowAttention(nn.Module):
                 bias = pointops.dot_prod_with_idx(key.float(), i1, self.relative_pos_key_table.float(), rel)
         softmax_attn_flat = pointops.segment_softmax(attn_flat, off, bias)
         if self.rel_value:
-            x = pointops.attention_step2_with_rel_pos_value_v2(softmax_attn_flat, value.float(), off, idx.n_max, i1,
-                                                               self.relative_pos_value_table.float(), rel)
+            x = pointops.window_aggregate(softmax_attn_flat, value.float(), self.relative_pos_value_table.float(), idx)
         else:
             if idx.index_0 is None:
                 idx.index_0 = torch.repeat_interleave(torch.arange(N, device=off.device, dtype=torch.int32),

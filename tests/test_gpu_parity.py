@@ -65,6 +65,31 @@ def run_layer(dev, requires_grad=True):
     return res
 
 
+def run_layer_fused(dev):
+    """Same path through the fused entry points (window_logits + segment_softmax + window_aggregate)."""
+    from stratified_transformer_b200 import pointops
+    from stratified_transformer_b200.index import PairIndex
+    q, k, v = (dev[n].clone().requires_grad_(True) for n in ("q", "k", "v"))
+    tq, tk, tv = (dev[n].clone().requires_grad_(True) for n in ("tq", "tk", "tv"))
+    off, i1, rel = dev["offsets"], dev["i1"], dev["rel"].contiguous()
+    pi = PairIndex(off, i1, rel, 0, int(i1.numel()))
+    s = pointops.window_logits(q, k, tq, tk, pi)
+    p = pointops.segment_softmax(s, off)
+    out = pointops.window_aggregate(p, v, tv, pi)
+    out.backward(dev["g_out"])
+    return dict(s=s, p=p, out=out, gq=q.grad, gk=k.grad, gv=v.grad, gtq=tq.grad, gtk=tk.grad, gtv=tv.grad)
+
+
+@pytest.mark.parametrize("N,M,h,d,L", [(3500, 80000, 6, 16, 31), (700, 30000, 3, 16, 64), (500, 9000, 4, 32, 20),
+                                       (300, 6000, 24, 16, 80), (64, 40, 2, 16, 5)])
+def test_fused_entry_points_vs_oracle(N, M, h, d, L):
+    cpu, dev = make_case(N, M, h, d, L, seed=3, dist="randn")
+    got = run_layer_fused(dev)
+    want = oracle_layer(cpu)
+    for key in ("s", "p", "out", "gq", "gk", "gv", "gtq", "gtk", "gtv"):
+        close(got[key], want[key], key, tol=2e-4 if key.startswith("gt") else TOL)
+
+
 def oracle_layer(cpu):
     d64 = {n: (t.double() if t.is_floating_point() else t) for n, t in cpu.items()}
     return ao.layer_fwd_bwd(d64["q"], d64["k"], d64["v"], d64["offsets"], d64["i1"], d64["tq"], d64["tk"], d64["tv"],

@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--points", type=int, default=80000)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="build the geometry serially inside the step instead of prefetching it on a side stream")
     ap.add_argument("--no-profile", action="store_true", help="do not bracket kernels with CUDA events in the timed region")
     ap.add_argument("--cpu-sample-points", type=int, default=0, help="points of the CPU sample scene (0 = auto)")
     return ap.parse_args()
@@ -143,6 +144,8 @@ def workload_config(a, note=None):
         "scenes_per_gpu": a.scenes, "points_per_scene": a.points, "head_dim": HEAD_DIM,
         "l2_policy": "inputs larger than L2 (q/k/v + pair arrays of layer 0 alone exceed 2 GB)",
         "parallelism": f"dp{a.gpus} by scene",
+        "geometry": "serial inside the step" if getattr(a, "no_overlap", False) else
+                    "FPS + pair lists of batch t+1 computed on a side stream during the attention of batch t (one full geometry per step)",
     }
     if note:
         cfg["note"] = note
@@ -220,16 +223,16 @@ def build_inputs(a, rank, dev):
     return levels, torch.from_numpy(rgb)
 
 
-def device_step(levels, grads_out):
+def device_step(levels, grads_out, geo=None):
     """One pass of the hot path with device-resident operands through the extension-level API (fused entry points:
     logits = q.k + rel-pos bias in one pass, segment softmax, aggregation; and their single-pass gradients)."""
     import ctypes
     from stratified_transformer_b200 import _cabi, index, pointops2_cuda as ext
     stream = torch.cuda.current_stream().cuda_stream
-    for lv in levels:
+    for lvl, lv in enumerate(levels):
         cfg = lv["cfg"]
         h, L = cfg["h"], lv["L"]
-        li = index.build_layer_index(lv["xyz"], lv["offset"], cfg["window"], cfg["quant"], DS_SCALE)
+        li = geo[lvl] if geo is not None else index.build_layer_index(lv["xyz"], lv["offset"], cfg["window"], cfg["quant"], DS_SCALE)
         q, k, v, g = lv["q"], lv["k"], lv["v"], lv["g"]
         N = q.shape[0]
         dev = q.device
@@ -274,13 +277,13 @@ class HotPathModel(torch.nn.Module):
             torch.nn.ModuleList([WindowAttention(c["C"], c["window"], c["h"], c["quant"], rel_query=True, rel_key=True,
                                                  rel_value=True) for _ in range(c["depth"])]) for c in LAYERS])
 
-    def forward(self, feat6, xyzs, offsets, sub_idx):
+    def forward(self, feat6, xyzs, offsets, sub_idx, geo=None):
         from stratified_transformer_b200 import index
         feats = self.stem(feat6)
         for lvl, cfg in enumerate(LAYERS):
             if lvl > 0:
                 feats = self.down[lvl - 1](feats[sub_idx[lvl].long()])
-            li = index.build_layer_index(xyzs[lvl], offsets[lvl], cfg["window"], cfg["quant"], DS_SCALE)
+            li = geo[lvl] if geo is not None else index.build_layer_index(xyzs[lvl], offsets[lvl], cfg["window"], cfg["quant"], DS_SCALE)
             for blk, attn in enumerate(self.blocks[lvl]):
                 feats = feats + attn(feats, xyzs[lvl], li.for_block(blk))
         return feats.float().pow(2).mean()
@@ -313,8 +316,26 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    from stratified_transformer_b200 import index as st_index
+    geo_cfgs = [(lv["cfg"]["window"], lv["cfg"]["quant"], DS_SCALE, lv["L"]) for lv in levels]
+    xyzs_d = [lv["xyz"] for lv in levels]
+    offs_d = [lv["offset"] for lv in levels]
+    offs_h = [lv["offset"].cpu().tolist() for lv in levels]
+    pf = None
+    if not a.no_overlap:
+        # geometry (FPS + pair lists) of the NEXT batch runs on a side stream under the attention of the current one;
+        # every step still computes one complete geometry from the coordinates
+        pf = st_index.GeometryPrefetcher(geo_cfgs, dev)
+        pf.submit(xyzs_d, offs_d, offs_h)
+
     def one_step():
-        grads = device_step(levels, [])
+        geo = None
+        if pf is not None:
+            geo = pf.take()
+            pf.submit(xyzs_d, offs_d, offs_h)
+        grads = device_step(levels, [], geo)
+        if pf is not None:
+            pf.complete()
         if dist is not None:   # training only: data-parallel gradient all-reduce of the attention parameters
             flat = torch.cat([t.reshape(-1) for trip in grads for t in trip])
             dist.all_reduce(flat)
@@ -361,14 +382,36 @@ def main():
         h2d = host["feat6"].numel() * 4 + sum(x.numel() * 4 for x in host["xyz"]) + sum(o.numel() * 4 for o in host["off"]) + \
             sum(s.numel() * 4 for s in host["sub"] if s is not None)
 
+        main = torch.cuda.current_stream()
+        pf2 = None if a.no_overlap else st_index.GeometryPrefetcher(geo_cfgs, dev)
+
+        def upload(stream):
+            with torch.cuda.stream(stream):
+                d = dict(feat6=host["feat6"].to(dev, non_blocking=True),
+                         xyz=[x.to(dev, non_blocking=True) for x in host["xyz"]],
+                         off=[o.to(dev, non_blocking=True) for o in host["off"]],
+                         sub=[None if s is None else s.to(dev, non_blocking=True) for s in host["sub"]])
+            return d
+
+        state = {}
+        if pf2 is not None:
+            state["next"] = upload(pf2.side)
+            pf2.submit(state["next"]["xyz"], state["next"]["off"], offs_h)
+
         def e2e_step():
-            feat6 = host["feat6"].to(dev, non_blocking=True)
-            xyzs = [x.to(dev, non_blocking=True) for x in host["xyz"]]
-            offs = [o.to(dev, non_blocking=True) for o in host["off"]]
-            subs = [None if s is None else s.to(dev, non_blocking=True) for s in host["sub"]]
+            if pf2 is not None:   # inputs + geometry of this batch were prefetched during the previous step
+                cur, geo = state["next"], pf2.take()
+                for t in [cur["feat6"]] + cur["xyz"] + cur["off"] + [s for s in cur["sub"] if s is not None]:
+                    t.record_stream(main)
+                state["next"] = upload(pf2.side)
+                pf2.submit(state["next"]["xyz"], state["next"]["off"], offs_h)
+            else:
+                cur, geo = upload(main), None
             model.zero_grad(set_to_none=True)
-            loss = model(feat6, xyzs, offs, subs)
+            loss = model(cur["feat6"], cur["xyz"], cur["off"], cur["sub"], geo)
             loss.backward()
+            if pf2 is not None:
+                pf2.complete()
             return float(loss.item())   # D2H read of the step result
 
         for _ in range(2):

@@ -140,6 +140,7 @@ class LayerIndex:
     FPS-sampled key candidates and the two pair lists (even / odd blocks)."""
     downsample_idx: torch.Tensor | None
     parity: tuple
+    ready: object = None      # CUDA event recorded when the index was produced on a side stream
 
     def for_block(self, i: int) -> PairIndex:
         return self.parity[i % 2]
@@ -156,3 +157,130 @@ def build_layer_index(xyz: torch.Tensor, offset: torch.Tensor, window_size: floa
     ws = torch.empty(_cabi.load().stb200_pair_builder_workspace_bytes(xyz.shape[0]), dtype=torch.uint8, device=xyz.device)
     built = {p: build_stratified_index(xyz, offset, window_size, quant_size, ds_idx, p, want_index_0, ws) for p in parities}
     return LayerIndex(ds_idx, tuple(built.get(p) for p in (0, 1)))
+
+
+# ------------------------------------------------------------------------------------------------
+# Split-phase construction + prefetching.  The geometry of a batch (FPS, window partition, pair lists) depends only
+# on coordinates, never on features, so a training loop can compute it for batch t+1 on a side stream while the
+# attention of batch t runs (the reference does its geometric pre-step, tp.ball_query, in the data loop for the same
+# reason: train.py:323-325).  The only host round trip of the builder (reading M to allocate the pair arrays) is
+# split off: `start` enqueues everything up to the per-query counts without blocking the host, `finish` blocks on
+# an event that has usually fired long ago, then enqueues the fill / transposed CSR / packing kernels.
+class PendingLayerIndex:
+    def __init__(self, xyz, offset, window_size, quant_size, downsample_scale, offset_host, want_index_0=False, L=None):
+        self.xyz, self.window_size, self.quant_size, self.want_index_0, self.L = xyz, window_size, quant_size, want_index_0, L
+        dev = xyz.device
+        N, b = xyz.shape[0], len(offset_host)
+        self.N = N
+        offset = offset.to(device=dev, dtype=torch.int32).contiguous()
+        lib = _cabi.load()
+        self.ds_idx = None
+        m = 0
+        if downsample_scale is not None:
+            sizes = [int(offset_host[0])] + [int(offset_host[i] - offset_host[i - 1]) for i in range(1, b)]
+            new_counts = [n // downsample_scale + 1 for n in sizes]
+            m = sum(new_counts)
+            new_offset = torch.tensor(new_counts, dtype=torch.int32).cumsum(0).to(torch.int32).to(dev, non_blocking=True)
+            self.ds_idx = torch.empty(m, dtype=torch.int32, device=dev)
+            ext.furthestsampling_cuda(b, max(sizes), xyz, offset, new_offset, None, self.ds_idx)
+            self._keep = (new_offset,)
+        nbytes = lib.stb200_pair_builder_workspace_bytes(N)
+        self.parts = []
+        for parity in (0, 1):
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            offsets = torch.empty(N + 1, dtype=torch.int32, device=dev)
+            totals = torch.empty(4, dtype=torch.int32, device=dev)
+            _cabi.call("stb200_stratified_pairs_count", N, b, xyz.data_ptr(), offset.data_ptr(), float(window_size), parity,
+                       None if self.ds_idx is None else self.ds_idx.data_ptr(), m, ws.data_ptr(), nbytes, offsets.data_ptr(),
+                       totals.data_ptr(), _stream())
+            host = torch.empty(4, dtype=torch.int32, pin_memory=True)
+            host.copy_(totals, non_blocking=True)
+            self.parts.append((ws, offsets, totals, host))
+        self.m = m
+        self.offset = offset
+        self.counted = torch.cuda.current_stream().record_event()
+
+    def finish(self) -> "LayerIndex":
+        """Call under the same stream as the constructor."""
+        self.counted.synchronize()
+        dev = self.xyz.device
+        built = []
+        for ws, offsets, totals, host in self.parts:
+            M, n_max, err, _ = host.tolist()
+            if err:
+                raise _cabi.Stb200Error("pair builder: window grid has more than 2^32 cells")
+            index_1 = torch.empty(M, dtype=torch.int32, device=dev)
+            rel_idx = torch.empty(M, 3, dtype=torch.int32, device=dev)
+            index_0 = torch.empty(M, dtype=torch.int32, device=dev) if self.want_index_0 else None
+            if M:
+                _cabi.call("stb200_stratified_pairs_fill", self.N, self.xyz.data_ptr(), float(2 * self.window_size),
+                           float(self.quant_size), int(self.m > 0), ws.data_ptr(), ws.numel(), offsets.data_ptr(),
+                           index_1.data_ptr(), rel_idx.data_ptr(), None if index_0 is None else index_0.data_ptr(), M, _stream())
+            pi = PairIndex(offsets, index_1, rel_idx, int(n_max), int(M), index_0)
+            if self.L is not None:
+                pi.c_struct(self.L, backward=True)   # transposed CSR + packed bins, eagerly, on this stream
+            built.append(pi)
+        self.parts = None
+        li = LayerIndex(self.ds_idx, tuple(built))
+        li.ready = torch.cuda.current_stream().record_event()
+        return li
+
+
+def record_stream(li: "LayerIndex", stream) -> None:
+    """Tell the caching allocator that `stream` consumes the index tensors (they were allocated on another stream)."""
+    for pi in li.parity:
+        ts = [pi.index_0_offsets, pi.index_1, pi.rel_idx, pi.index_0]
+        if pi._tcsr is not None:
+            ts += [pi._tcsr.t_offsets, pi._tcsr.t_pair, pi._tcsr.t_index0]
+        for a, b in pi._packed.values():
+            ts += [a, b]
+        for t in ts:
+            if t is not None:
+                t.record_stream(stream)
+    if li.downsample_idx is not None:
+        li.downsample_idx.record_stream(stream)
+
+
+class GeometryPrefetcher:
+    """Double-buffered geometry pipeline for a stack of layers.
+
+        pf = GeometryPrefetcher(layer_cfgs)          # [(window, quant, downsample_scale, table_len), ...]
+        pf.submit(xyzs, offsets, offsets_host)        # batch 0
+        for batch in loader:
+            geo = pf.take()                           # list of LayerIndex for the current batch (main stream waits on it)
+            pf.submit(next xyzs, ...)                 # geometry of the next batch starts on the side stream
+            ... enqueue attention of the current batch on the main stream ...
+            pf.complete()                             # host: wait for the counts, enqueue fill / transpose / pack
+    """
+
+    def __init__(self, layer_cfgs, device=None):
+        self.cfgs = layer_cfgs
+        self.side = torch.cuda.Stream(device=device)
+        self.pending = None
+        self.done = None
+
+    def submit(self, xyzs, offsets, offsets_host):
+        main = torch.cuda.current_stream()
+        self.side.wait_stream(main)           # inputs produced on the main stream are visible
+        with torch.cuda.stream(self.side):
+            self.pending = [PendingLayerIndex(x, o, w, q, ds, oh, L=L)
+                            for x, o, oh, (w, q, ds, L) in zip(xyzs, offsets, offsets_host, self.cfgs)]
+        for x in xyzs:
+            x.record_stream(self.side)
+
+    def complete(self):
+        if self.pending is None:
+            return
+        with torch.cuda.stream(self.side):
+            self.done = [p.finish() for p in self.pending]
+        self.pending = None
+
+    def take(self):
+        if self.done is None:
+            self.complete()
+        geo, self.done = self.done, None
+        main = torch.cuda.current_stream()
+        for li in geo:
+            main.wait_event(li.ready)
+            record_stream(li, main)
+        return geo

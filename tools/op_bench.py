@@ -84,10 +84,13 @@ def main():
         "rpe_bwd": lambda: ext.dot_prod_with_idx_backward_cuda_v3(N, M, h, d, 0, gs, q, off, k, i1, tq, tk, rel_d, gq2, gk2, gtq, gtk, tc),
         "step1_bwd": lambda: ext.attention_step1_backward_cuda_v2(N, M, h, C, 0, gs, off, i1, q, k, gq, gk, tc),
     }
+    i0 = torch.repeat_interleave(torch.arange(N, device=dev, dtype=torch.int32), (off[1:] - off[:-1]).long())
+    ops["v1_step1_bwd(red.v4 scatter)"] = lambda: ext.attention_step1_backward_cuda(N, M, h, C, gs, i0, i1, q, k, gq, gk)
+    ops["v1_step2_fwd(red.v4 scatter)"] = lambda: ext.attention_step2_forward_cuda(N, M, h, C, p, v, i0, i1, out)
     res = {"N": N, "M": M, "h": h, "transpose_csr_ms": t_build}
     for name, fn in ops.items():
         res[name + "_ms"] = timed(fn, flush=flush)
-    res["total_ms"] = sum(v for kk, v in res.items() if kk.endswith("_ms") and kk != "transpose_csr_ms")
+    res["total_ms"] = sum(v for kk, v in res.items() if kk.endswith("_ms") and kk != "transpose_csr_ms" and not kk.startswith("v1_"))
     kap = M / N
     fwd_b = 4 * (6 * C + 9 * kap + 5 * kap * h + 4) * N
     bwd_b = 4 * (11 * C + 9 * kap + 7 * kap * h + 3) * N

@@ -101,3 +101,46 @@ class WindowAttention(nn.Module):
         x = self.proj(x)
         x = self.proj_drop(x)
         return x
+
+
+class SwinWindowAttention(WindowAttention):
+    """Mirror of the 3DSwin variant (/root/reference/model/swin3d_transformer.py:81-178): dense window pairs only,
+    tables of length 2*int(window/quant)-1, rel-pos index from per-point quantised coordinates (:151-154), forward
+    signature `(feats, xyz, index_0, index_0_offsets, n_max, index_1, shift_size)`."""
+
+    def __init__(self, dim, window_size, num_heads, quant_size, rel_query=True, rel_key=False, rel_value=False,
+                 qkv_bias=True, qk_scale=None, attn_drop=0., proj_drop=0.):
+        nn.Module.__init__(self)
+        self.dim = dim
+        self.window_size = window_size
+        self.num_heads = num_heads
+        head_dim = dim // num_heads
+        self.scale = qk_scale or head_dim ** -0.5
+        self.quant_size = quant_size
+        self.rel_query, self.rel_key, self.rel_value = rel_query, rel_key, rel_value
+        quant_grid_length = int(window_size / quant_size)
+        self.quant_grid_length = quant_grid_length
+
+        def table():
+            t = nn.Parameter(torch.zeros(2 * quant_grid_length - 1, num_heads, head_dim, 3))
+            nn.init.trunc_normal_(t, std=.02)
+            return t
+
+        if rel_query:
+            self.relative_pos_query_table = table()
+        if rel_key:
+            self.relative_pos_key_table = table()
+        if rel_value:
+            self.relative_pos_value_table = table()
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.attn_drop = nn.Dropout(attn_drop, inplace=True)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop, inplace=True)
+
+    def forward(self, feats, xyz, index_0, index_0_offsets, n_max, index_1, shift_size):
+        from .index import rel_pos_index_swin
+        shift = float(shift_size.flatten()[0]) if isinstance(shift_size, torch.Tensor) else float(shift_size)
+        off32, i1_32 = index_0_offsets.int().contiguous(), index_1.int().contiguous()
+        idx = PairIndex(off32, i1_32, None, 0, int(index_1.shape[0]), None if index_0 is None else index_0.int().contiguous())
+        idx.rel_idx = rel_pos_index_swin(xyz, off32, i1_32, self.window_size, self.quant_size, shift)
+        return WindowAttention.forward(self, feats, xyz, idx)

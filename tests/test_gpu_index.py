@@ -137,3 +137,41 @@ def test_window_attention_module_vs_oracle(golden_dir):
     ref.backward(gout.double().cpu())
     assert torch.allclose(out.detach().double().cpu(), ref.detach(), rtol=2e-4, atol=2e-5)
     assert torch.allclose(fd.grad.double().cpu(), f.grad, rtol=2e-3, atol=2e-5)
+
+
+def test_swin_window_attention_module(golden_dir):
+    """3DSwin variant: dense-only pairs from the builder, Swin rel-pos index, module forward/backward against the
+    oracle composition."""
+    from oracle import attention_oracle as ao
+    from stratified_transformer_b200.window_attention import SwinWindowAttention
+    g = np.load(os.path.join(golden_dir, "index_s3dis_small.npz"))
+    xyz, offset = g["xyz"], g["offset"]
+    torch.manual_seed(1)
+    C, h, w, quant = 96, 6, 0.16, 0.01
+    mod = SwinWindowAttention(C, w, h, quant, rel_query=True, rel_key=True, rel_value=True).cuda()
+    assert mod.relative_pos_query_table.shape[0] == 31
+    feats = torch.randn(xyz.shape[0], C)
+    pi = build(xyz, offset, w, None, None, 1, want_index_0=True)      # shifted windows
+    shift = 0.5 * np.float32(w)
+    fd = feats.cuda().requires_grad_(True)
+    out = mod(fd, torch.from_numpy(xyz).cuda(), pi.index_0.long(), pi.index_0_offsets.long(), pi.n_max, pi.index_1.long(),
+              torch.full((3,), float(shift)).cuda())
+    gout = torch.randn_like(out)
+    out.backward(gout)
+    i0 = pi.index_0.long().cpu(); i1 = pi.index_1.long().cpu()
+    r = torch.from_numpy(io.rel_pos_index_swin(xyz, i0.numpy(), i1.numpy(), w, quant, float(shift))).long()
+    assert int(r.min()) >= 0 and int(r.max()) <= 30
+    W = {k: v.detach().double().cpu() for k, v in mod.state_dict().items()}
+    f = feats.double().requires_grad_(True)
+    qkv = (f @ W["qkv.weight"].T + W["qkv.bias"]).reshape(-1, 3, h, C // h).permute(1, 0, 2, 3)
+    q, k, v = qkv[0] * mod.scale, qkv[1], qkv[2]
+    tq, tk, tv = (W[f"relative_pos_{n}_table"] for n in ("query", "key", "value"))
+    s = (q[i0] * k[i1]).sum(-1) + (q[i0] * ao.table_sum(tq, r) + k[i1] * ao.table_sum(tk, r)).sum(-1)
+    mx = s.detach().new_full((f.shape[0], h), -1e30).scatter_reduce(0, i0[:, None].expand(-1, h), s.detach(), "amax")
+    ex = torch.exp(s - mx[i0])
+    p = ex / torch.zeros(f.shape[0], h, dtype=torch.float64).index_add(0, i0, ex)[i0]
+    x = torch.zeros(f.shape[0], h, C // h, dtype=torch.float64).index_add(0, i0, p.unsqueeze(-1) * (v[i1] + ao.table_sum(tv, r)))
+    ref = x.reshape(-1, C) @ W["proj.weight"].T + W["proj.bias"]
+    ref.backward(gout.double().cpu())
+    assert torch.allclose(out.detach().double().cpu(), ref.detach(), rtol=2e-4, atol=2e-5)
+    assert torch.allclose(fd.grad.double().cpu(), f.grad, rtol=2e-3, atol=2e-5)

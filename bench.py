@@ -306,6 +306,8 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=dev)
 
     levels, rgb = build_inputs(a, rank, dev)

@@ -170,7 +170,8 @@ int stb200_stratified_pairs_count(int N, int b, const float *xyz, const int *off
                                   int *index0_offsets, int *totals, void *stream);
 int stb200_stratified_pairs_fill(int N, const float *xyz, float window_size_x2, float quant_size, int has_sparse,
                                  void *workspace, size_t workspace_bytes, const int *index0_offsets, int *index_1,
-                                 int *rel_idx, int *index_0, int M, void *stream);
+                                 int *rel_idx, int *index_0, int *row_order /* [N] points sorted by window, may be NULL */,
+                                 int M, void *stream);
 
 /* Relative-position index of an existing CSR pair list.
  * Stratified: idx = ((round((xyz[i0]-xyz[i1])*1e5)/1e5) + 2w - 1e-4) // quant  (stratified_transformer.py:186-188)
@@ -199,6 +200,8 @@ typedef struct stb200_index {
     const int *t_index0;       /* [M]   */
     const unsigned *rel_packed;   /* [M] optional */
     const unsigned *t_rel_packed; /* [M] optional, bins of pair t_pair[t] */
+    const int *row_order;         /* [N] optional: process rows in this order (e.g. points sorted by window, from the
+                                     pair builder) so that neighbouring warps gather the same k/v rows */
 } stb200_index;
 
 /* out[i] = r0 | r1 << 10 | r2 << 20 of pair (perm ? perm[i] : i), bins clamped to [0, L) */

@@ -18,7 +18,8 @@ class IndexStruct(ctypes.Structure):
     """mirror of `stb200_index` (include/stb200.h)"""
     _fields_ = [("N", ctypes.c_int), ("M", ctypes.c_int), ("index0_offsets", ctypes.c_void_p), ("index1", ctypes.c_void_p),
                 ("rel_idx", ctypes.c_void_p), ("t_offsets", ctypes.c_void_p), ("t_pair", ctypes.c_void_p),
-                ("t_index0", ctypes.c_void_p), ("rel_packed", ctypes.c_void_p), ("t_rel_packed", ctypes.c_void_p)]
+                ("t_index0", ctypes.c_void_p), ("rel_packed", ctypes.c_void_p), ("t_rel_packed", ctypes.c_void_p),
+                ("row_order", ctypes.c_void_p)]
 
 
 _IX = ctypes.POINTER(IndexStruct)
@@ -44,7 +45,7 @@ _SIGNATURES = {
     "stb200_attention_step2_with_rel_pos_value_backward": [_c_int] * 5 + [P] * 11,
     "stb200_furthestsampling": [_c_int, _c_int] + [P] * 6,
     "stb200_stratified_pairs_count": [_c_int, _c_int, P, P, ctypes.c_float, _c_int, P, _c_int, P, _c_size_t, P, P, P],
-    "stb200_stratified_pairs_fill": [_c_int, P, ctypes.c_float, ctypes.c_float, _c_int, P, _c_size_t, P, P, P, P, _c_int, P],
+    "stb200_stratified_pairs_fill": [_c_int, P, ctypes.c_float, ctypes.c_float, _c_int, P, _c_size_t, P, P, P, P, P, _c_int, P],
     "stb200_rel_pos_index_stratified": [_c_int, P, P, P, ctypes.c_float, ctypes.c_float, P, P],
     "stb200_pack_rel": [_c_int, _c_int, P, P, P, P],
     "stb200_window_logits_forward": [_IX, _c_int, _c_int, _c_int] + [P] * 6,

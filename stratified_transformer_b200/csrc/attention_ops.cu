@@ -20,6 +20,8 @@
 //   * table gradients use  gT[l,h,c,a] = sum_n X[n,h,c] * W_a[n,l,h],  W_a[n,l,h] = sum_{m in seg(n), r[m,a]=l} w[m,h]:
 //     a per-row histogram (3 scalar adds per pair-head instead of 3*d atomics) followed by a register-tiled
 //     fp32 outer-product accumulation; one flush of red.global.add per CTA at the end.
+#include <cstdlib>
+
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -39,9 +41,12 @@ struct SegParams {
     const int *pair_id;    // pair id per segment slot (transposed CSR) or null
     const float *Tx, *Ty;  // rel-pos tables [L, h, D, 3]
     const int *rel_idx;    // [M, 3]
+    const int *row_order;   // optional: process rows in this order (window-sorted => neighbouring warps share gathered rows in L1)
     const unsigned *packed; // optional: the three bins of each segment slot packed 10 bits each (replaces rel_idx)
     float *out;
     int accumulate;
+    const float *T2;       // table_grad FOLD: table whose rows multiply the histograms -> row gradients
+    float *out2;           // table_grad FOLD: [N, h, D] gradient rows, added to with red.global.add
 };
 
 // Copy one head group of a [L,h,D,3] table into shared memory as [axis][l][hh][c].
@@ -105,7 +110,8 @@ __global__ void __launch_bounds__(kThreads) seg_dot_kernel(const SegParams p) {
 
     for (int base_n = blockIdx.x * kRowsPerChunk; base_n < p.N; base_n += gridDim.x * kRowsPerChunk) {
         const int end_n = min(p.N, base_n + kRowsPerChunk);
-        for (int n = base_n + warp; n < end_n; n += nwarps) {
+        for (int nn = base_n + warp; nn < end_n; nn += nwarps) {
+            const int n = p.row_order ? __ldg(p.row_order + nn) : nn;
             const int start = __ldg(p.offsets + n), len = __ldg(p.offsets + n + 1) - start;
             if (len <= 0) continue;
             __syncwarp();
@@ -180,7 +186,8 @@ __global__ void __launch_bounds__(kThreads) seg_reduce_kernel(const SegParams p)
 
     for (int base_n = blockIdx.x * kRowsPerChunk; base_n < p.N; base_n += gridDim.x * kRowsPerChunk) {
         const int end_n = min(p.N, base_n + kRowsPerChunk);
-        for (int n = base_n + warp; n < end_n; n += nwarps) {
+        for (int nn = base_n + warp; nn < end_n; nn += nwarps) {
+            const int n = p.row_order ? __ldg(p.row_order + nn) : nn;
             const int start = __ldg(p.offsets + n), end = __ldg(p.offsets + n + 1);
             float4 acc[HG];
 #pragma unroll
@@ -274,7 +281,7 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], 
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-template <int D, int HGC, bool PERM, bool MULTI>
+template <int D, int HGC, bool PERM, bool MULTI, bool FOLD>
 __global__ void __launch_bounds__(kTGThreads(HGC), (D == 16 ? 2 : 1)) table_grad_kernel(const SegParams p, int row_pass_base, int Rpad) {
     extern __shared__ float4 smem4[];
     constexpr int NT = D / 8;                               // n-tiles (8 channels each)
@@ -290,6 +297,8 @@ __global__ void __launch_bounds__(kTGThreads(HGC), (D == 16 ? 2 : 1)) table_grad
     float *sw = Xs + HGC * kTQ * XP;                        // [HGC][kPC] weights
     unsigned *pk = reinterpret_cast<unsigned *>(sw + HGC * kPC);   // [kPC] r0 | r1<<8 | r2<<16
     int *soff = reinterpret_cast<int *>(pk + kPC);          // [kTQ + 1] offsets of the tile's rows
+    float *Tt = reinterpret_cast<float *>(soff + kTQ + 8);  // FOLD: [D][Rpad + 4] transposed table of the current head
+    const int RTP = Rpad + 4;
     const int tid = threadIdx.x, lane = tid % kWarp, warp = tid / kWarp, nthr = blockDim.x;
     const int gid = lane >> 2, tig = lane & 3;
 
@@ -352,6 +361,16 @@ __global__ void __launch_bounds__(kTGThreads(HGC), (D == 16 ? 2 : 1)) table_grad
         // ---- C += W^T X  (rows of W^T = table rows, k = tile rows, n = channels)
 #pragma unroll
         for (int hh = 0; hh < HGC; ++hh) {
+            if (FOLD) {   // transposed table of this head: Tt[c][(axis, l)], zero beyond the last table row
+                if (hh > 0) __syncthreads();
+                for (int i = tid; i < L * D * 3; i += nthr) {
+                    const int l = i / (D * 3), e = i - l * (D * 3);
+                    const int c = e / 3, a = e - c * 3;
+                    Tt[c * RTP + a * L + l] = __ldg(p.T2 + (size_t)(l * h + h0 + hh) * (D * 3) + e);
+                }
+                for (int i = tid; i < D * (Rpad - R); i += nthr) Tt[(i / (Rpad - R)) * RTP + R + i % (Rpad - R)] = 0.f;
+                __syncthreads();
+            }
 #pragma unroll
             for (int tp = 0; tp < TPW; ++tp) {
                 const int tile = warp + tp * NW;
@@ -371,6 +390,38 @@ __global__ void __launch_bounds__(kTGThreads(HGC), (D == 16 ? 2 : 1)) table_grad
                         mma_tf32(acc[hh][tp], al, bh);
                         mma_tf32(acc[hh][tp], ah, bl);
                         mma_tf32(acc[hh][tp], ah, bh);
+                    }
+                }
+            }
+            if (FOLD) {
+                // ---- G[t][c] = sum_rows W[row][t] * T[row][c]: the rel-pos part of the row gradient (grad_q / grad_k),
+                // (kTQ/16) x NT output tiles, the table-row range split in two halves -> 2 * (kTQ/16) * NT units per head,
+                // handed out from the last warp downwards (those warps own fewer table-gradient tiles)
+                constexpr int UNITS = 2 * (kTQ / 16) * NT;
+                const int ksteps = Rpad / 8;
+                for (int u = NW - 1 - warp; u < UNITS; u += NW) {
+                    const int half = u & 1, mt2 = (u >> 1) % (kTQ / 16), nt = (u >> 1) / (kTQ / 16);
+                    const int kb = half ? ksteps / 2 : 0, ke = half ? ksteps : ksteps / 2;
+                    float g[4] = {0.f, 0.f, 0.f, 0.f};
+                    const float *wa = W + (hh * Rpad + tig) * kTQP + mt2 * 16 + gid;
+                    const float *tb = Tt + (nt * 8 + gid) * RTP + tig;
+                    for (int ks = kb; ks < ke; ++ks) {
+                        const int k0 = ks * 8;
+                        unsigned ah[4], al[4], bh[2], bl[2];
+                        split_tf32(wa[k0 * kTQP], ah[0], al[0]);
+                        split_tf32(wa[k0 * kTQP + 8], ah[1], al[1]);
+                        split_tf32(wa[(k0 + 4) * kTQP], ah[2], al[2]);
+                        split_tf32(wa[(k0 + 4) * kTQP + 8], ah[3], al[3]);
+                        split_tf32(tb[k0], bh[0], bl[0]);
+                        split_tf32(tb[k0 + 4], bh[1], bl[1]);
+                        mma_tf32(g, al, bh);
+                        mma_tf32(g, ah, bl);
+                        mma_tf32(g, ah, bh);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int n = base_n + mt2 * 16 + gid + (c >= 2 ? 8 : 0);
+                        if (n < p.N) atomicAdd(p.out2 + ((size_t)n * h + h0 + hh) * D + nt * 8 + 2 * tig + (c & 1), g[c]);
                     }
                 }
             }
@@ -688,16 +739,19 @@ template <int D, int HGC, bool PERM>
 static int launch_table_grad_hg(const SegParams &p, int M, const char *name, cudaStream_t s) {
     const int R = 3 * p.L;
     const int Rpad = min(256, (R + 15) / 16 * 16);
-    const size_t smem = ((size_t)HGC * Rpad * kTQP + HGC * kTQ * (D + 8) + HGC * kPC + kPC + kTQ + 8) * sizeof(float);
-    auto kern = R <= 256 ? table_grad_kernel<D, HGC, PERM, false> : table_grad_kernel<D, HGC, PERM, true>;
-    if (int rc = prep_smem(table_grad_kernel<D, HGC, PERM, false>, smem)) return rc;
-    if (int rc = prep_smem(table_grad_kernel<D, HGC, PERM, true>, smem)) return rc;
+    const bool fold = p.T2 != nullptr;
+    STB200_REQUIRE(!fold || R <= 256, STB200_ERR_ARG, "folded row gradient needs a table of at most 85 rows");
+    const size_t smem = ((size_t)HGC * Rpad * kTQP + HGC * kTQ * (D + 8) + HGC * kPC + kPC + kTQ + 8 + (fold ? D * (Rpad + 4) : 0)) * sizeof(float);
+    void (*kern)(const SegParams, int, int) =
+        fold ? table_grad_kernel<D, HGC, PERM, false, true>
+             : (R <= 256 ? table_grad_kernel<D, HGC, PERM, false, false> : table_grad_kernel<D, HGC, PERM, true, false>);
+    if (int rc = prep_smem(kern, smem)) return rc;
     const int tiles = (p.N + kTQ - 1) / kTQ;
     const int groups = p.h / HGC;
-    const int ctas_per_sm = max(1, min(4, (int)((220 * 1024) / smem)));
+    const int ctas_per_sm = max(1, min(4, (int)((226 * 1024) / (smem + 1024))));
     const int gx = max(1, min(tiles, (kNumSMs * ctas_per_sm + groups - 1) / groups));
     for (int pass = 0; pass < R; pass += 256) {
-        KernelScope ks(name, seg_bytes(p, D, M, true, false, true, false, PERM, 1, false) - 4.0 * p.N * p.h * D, s);
+        KernelScope ks(name, seg_bytes(p, D, M, true, false, true, false, PERM, 1, false) - 4.0 * p.N * p.h * D + (fold ? 8.0 * p.N * p.h * D : 0.0), s);
         kern<<<dim3(gx, groups), kTGThreads(HGC), smem, s>>>(p, pass, Rpad);
     }
     return check_launch(name);
@@ -894,7 +948,7 @@ int stb200_window_logits_forward(const stb200_index *ix, int h, int hdim, int L,
     STB200_REQUIRE(L > 0 && L <= 1024 && q && k && table_q && table_k && logits, STB200_ERR_ARG, "null pointer or bad L");
     SegParams p{};
     p.N = ix->N; p.h = h; p.L = L; p.X = q; p.Y = k; p.offsets = ix->index0_offsets; p.gather_idx = ix->index1;
-    p.Tx = table_q; p.Ty = table_k; p.rel_idx = ix->rel_idx; p.packed = ix->rel_packed; p.out = logits;
+    p.Tx = table_q; p.Ty = table_k; p.rel_idx = ix->rel_idx; p.packed = ix->rel_packed; p.row_order = ix->row_order; p.out = logits;
     return launch_seg_dot<true, true, true>(hdim, p, ix->M, "seg_dot[logits_fwd]", (cudaStream_t)stream);
 }
 
@@ -908,17 +962,33 @@ int stb200_window_logits_backward(const stb200_index *ix, int h, int hdim, int L
     cudaStream_t s = (cudaStream_t)stream;
     const int M = ix->M;
     SegParams p{};
-    p.N = ix->N; p.h = h; p.L = L; p.w = grad_logits; p.rel_idx = ix->rel_idx;
+    p.N = ix->N; p.h = h; p.L = L; p.w = grad_logits; p.rel_idx = ix->rel_idx; p.row_order = ix->row_order;
+    // Optional (STB200_FOLD_ROWGRAD=1): take the rel-pos part of grad_q / grad_k from the histograms inside the
+    // table-gradient kernels (G = W^T T on the tensor cores) instead of per-pair table look-ups.  Measured neutral on
+    // B200 at the S3DIS shapes (the look-up kernels get 2.5x faster, the table-gradient kernels 1.7x slower), so off by default.
+    static const bool fold_env = getenv("STB200_FOLD_ROWGRAD") && atoi(getenv("STB200_FOLD_ROWGRAD")) != 0;
+    const bool fold = fold_env && 3 * L <= 256;
     // grad_q = sum g * (k[i1] + Eq)                                              (overwritten)
     p.packed = ix->rel_packed; p.offsets = ix->index0_offsets; p.gather_idx = ix->index1; p.Y = k; p.Tx = table_q; p.out = grad_q;
-    if (int rc = launch_seg_reduce<true, true, false>(hdim, p, M, "seg_reduce[logits_bwd_gq]", s)) return rc;
-    p.X = q; p.out = grad_table_q;
+    if (fold) {
+        if (int rc = launch_seg_reduce<true, false, false>(hdim, p, M, "seg_reduce[logits_bwd_gq]", s)) return rc;
+    } else {
+        if (int rc = launch_seg_reduce<true, true, false>(hdim, p, M, "seg_reduce[logits_bwd_gq]", s)) return rc;
+    }
+    p.X = q; p.out = grad_table_q; p.row_order = nullptr;
+    if (fold) { p.T2 = table_q; p.out2 = grad_q; }
     if (int rc = launch_table_grad<false>(hdim, p, M, "table_grad[logits_bwd_gtq]", s)) return rc;
     // grad_k += sum over incoming pairs g * (q[i0] + Ek)                          (accumulated)
+    p.T2 = nullptr; p.out2 = nullptr; p.row_order = ix->row_order;
     p.packed = ix->t_rel_packed; p.offsets = ix->t_offsets; p.pair_id = ix->t_pair; p.gather_idx = ix->t_index0;
     p.Y = q; p.Tx = table_k; p.out = grad_k; p.accumulate = 1;
-    if (int rc = launch_seg_reduce<true, true, true>(hdim, p, M, "seg_reduce_t[logits_bwd_gk]", s)) return rc;
-    p.X = k; p.out = grad_table_k;
+    if (fold) {
+        if (int rc = launch_seg_reduce<true, false, true>(hdim, p, M, "seg_reduce_t[logits_bwd_gk]", s)) return rc;
+    } else {
+        if (int rc = launch_seg_reduce<true, true, true>(hdim, p, M, "seg_reduce_t[logits_bwd_gk]", s)) return rc;
+    }
+    p.X = k; p.out = grad_table_k; p.row_order = nullptr;
+    if (fold) { p.T2 = table_k; p.out2 = grad_k; }
     return launch_table_grad<true>(hdim, p, M, "table_grad_t[logits_bwd_gtk]", s);
 }
 
@@ -929,7 +999,7 @@ int stb200_window_aggregate_forward(const stb200_index *ix, int h, int hdim, int
     STB200_REQUIRE(L > 0 && L <= 1024 && output && (ix->M == 0 || (attn && v && table_v)), STB200_ERR_ARG, "null pointer or bad L");
     SegParams p{};
     p.N = ix->N; p.h = h; p.L = L; p.w = attn; p.Y = v; p.offsets = ix->index0_offsets; p.gather_idx = ix->index1;
-    p.Tx = table_v; p.rel_idx = ix->rel_idx; p.packed = ix->rel_packed; p.out = output;
+    p.Tx = table_v; p.rel_idx = ix->rel_idx; p.packed = ix->rel_packed; p.row_order = ix->row_order; p.out = output;
     return launch_seg_reduce<true, true, false>(hdim, p, ix->M, "seg_reduce[aggregate_fwd]", (cudaStream_t)stream);
 }
 
@@ -943,7 +1013,7 @@ int stb200_window_aggregate_backward(const stb200_index *ix, int h, int hdim, in
     cudaStream_t s = (cudaStream_t)stream;
     const int M = ix->M;
     SegParams p{};
-    p.N = ix->N; p.h = h; p.L = L; p.rel_idx = ix->rel_idx; p.packed = ix->rel_packed;
+    p.N = ix->N; p.h = h; p.L = L; p.rel_idx = ix->rel_idx; p.packed = ix->rel_packed; p.row_order = ix->row_order;
     p.X = grad_out; p.Y = v; p.offsets = ix->index0_offsets; p.gather_idx = ix->index1; p.Tx = table_v; p.out = grad_attn;
     if (M > 0)
         if (int rc = launch_seg_dot<true, true, false>(hdim, p, M, "seg_dot[aggregate_bwd_gattn]", s)) return rc;

@@ -431,7 +431,7 @@ int stb200_stratified_pairs_count(int N, int b, const float *xyz, const int *off
 
 int stb200_stratified_pairs_fill(int N, const float *xyz, float window_size_x2, float quant_size, int has_sparse,
                                  void *workspace, size_t workspace_bytes, const int *index0_offsets, int *index_1,
-                                 int *rel_idx, int *index_0, int M, void *stream) {
+                                 int *rel_idx, int *index_0, int *row_order, int M, void *stream) {
     STB200_REQUIRE(N > 0 && xyz && workspace && index0_offsets && index_1, STB200_ERR_ARG, "null pointer / bad N");
     STB200_REQUIRE(workspace_bytes >= stb200_pair_builder_workspace_bytes(N), STB200_ERR_WORKSPACE, "workspace too small");
     BuilderState st;
@@ -444,6 +444,7 @@ int stb200_stratified_pairs_fill(int N, const float *xyz, float window_size_x2, 
             N, xyz, index0_offsets, st.win_s, st.win_l, st.wstart_s, st.wstart_l, st.order_s, st.spos, st.samp, st.wc,
             has_sparse, window_size_x2, quant_size, index_1, rel_idx, index_0);
     }
+    if (row_order) cudaMemcpyAsync(row_order, st.order_s, (size_t)N * sizeof(int), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
     return check_launch("stratified_pairs_fill");
 }
 

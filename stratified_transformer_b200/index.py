@@ -31,6 +31,7 @@ class PairIndex:
     n_max: int
     M: int
     index_0: torch.Tensor | None = None    # [M]   only when asked for (v1 ops, scatter_softmax callers)
+    row_order: torch.Tensor | None = None  # [N]   points sorted by window (locality hint for the fused entry points)
     _tcsr: ext.TransposedCSR | None = field(default=None, repr=False)
     _packed: dict = field(default_factory=dict, repr=False)   # L -> (rel_packed, t_rel_packed | None)
 
@@ -60,7 +61,8 @@ class PairIndex:
         if backward and ent[1] is None:
             ent[1] = self._pack(L, self.tcsr.t_pair)
         st = _cabi.IndexStruct(self.N, self.M, self.index_0_offsets.data_ptr(), self.index_1.data_ptr(),
-                               self.rel_idx.data_ptr(), None, None, None, ent[0].data_ptr(), None)
+                               self.rel_idx.data_ptr(), None, None, None, ent[0].data_ptr(), None,
+                               None if self.row_order is None else self.row_order.data_ptr())
         if backward:
             t = self.tcsr
             st.t_offsets, st.t_pair, st.t_index0 = t.t_offsets.data_ptr(), t.t_pair.data_ptr(), t.t_index0.data_ptr()
@@ -104,13 +106,14 @@ def build_stratified_index(xyz: torch.Tensor, offset: torch.Tensor, window_size:
     index_1 = torch.empty(M, dtype=torch.int32, device=dev)
     rel_idx = torch.empty(M, 3, dtype=torch.int32, device=dev) if quant_size is not None else None
     index_0 = torch.empty(M, dtype=torch.int32, device=dev) if want_index_0 else None
+    row_order = torch.empty(N, dtype=torch.int32, device=dev)
     if M:
         _cabi.call("stb200_stratified_pairs_fill", N, xyz.data_ptr(), float(2 * window_size),
                    float(quant_size if quant_size is not None else 1.0), int(m > 0), workspace.data_ptr(),
                    workspace.numel(), offsets.data_ptr(), index_1.data_ptr(),
                    None if rel_idx is None else rel_idx.data_ptr(), None if index_0 is None else index_0.data_ptr(),
-                   M, _stream())
-    return PairIndex(offsets, index_1, rel_idx, int(n_max), int(M), index_0)
+                   row_order.data_ptr(), M, _stream())
+    return PairIndex(offsets, index_1, rel_idx, int(n_max), int(M), index_0, row_order if M else None)
 
 
 def rel_pos_index_stratified(xyz, index_0_offsets, index_1, window_size: float, quant_size: float) -> torch.Tensor:
@@ -212,11 +215,13 @@ class PendingLayerIndex:
             index_1 = torch.empty(M, dtype=torch.int32, device=dev)
             rel_idx = torch.empty(M, 3, dtype=torch.int32, device=dev)
             index_0 = torch.empty(M, dtype=torch.int32, device=dev) if self.want_index_0 else None
+            row_order = torch.empty(self.N, dtype=torch.int32, device=dev)
             if M:
                 _cabi.call("stb200_stratified_pairs_fill", self.N, self.xyz.data_ptr(), float(2 * self.window_size),
                            float(self.quant_size), int(self.m > 0), ws.data_ptr(), ws.numel(), offsets.data_ptr(),
-                           index_1.data_ptr(), rel_idx.data_ptr(), None if index_0 is None else index_0.data_ptr(), M, _stream())
-            pi = PairIndex(offsets, index_1, rel_idx, int(n_max), int(M), index_0)
+                           index_1.data_ptr(), rel_idx.data_ptr(), None if index_0 is None else index_0.data_ptr(),
+                           row_order.data_ptr(), M, _stream())
+            pi = PairIndex(offsets, index_1, rel_idx, int(n_max), int(M), index_0, row_order if M else None)
             if self.L is not None:
                 pi.c_struct(self.L, backward=True)   # transposed CSR + packed bins, eagerly, on this stream
             built.append(pi)
@@ -229,7 +234,7 @@ class PendingLayerIndex:
 def record_stream(li: "LayerIndex", stream) -> None:
     """Tell the caching allocator that `stream` consumes the index tensors (they were allocated on another stream)."""
     for pi in li.parity:
-        ts = [pi.index_0_offsets, pi.index_1, pi.rel_idx, pi.index_0]
+        ts = [pi.index_0_offsets, pi.index_1, pi.rel_idx, pi.index_0, pi.row_order]
         if pi._tcsr is not None:
             ts += [pi._tcsr.t_offsets, pi._tcsr.t_pair, pi._tcsr.t_index0]
         for a, b in pi._packed.values():

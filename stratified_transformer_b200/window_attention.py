@@ -62,9 +62,13 @@ class WindowAttention(nn.Module):
             idx.rel_idx = rel_pos_index_stratified(xyz, idx.index_0_offsets, idx.index_1, self.window_size, self.quant_size)
         N, C = feats.shape
         h = self.num_heads
-        qkv = self.qkv(feats).reshape(N, 3, h, C // h).permute(1, 0, 2, 3).contiguous()
-        query, key, value = qkv[0], qkv[1], qkv[2]
-        query = query * self.scale
+        # same math as `qkv(feats).reshape(N,3,h,d).permute(1,0,2,3)` followed by `query * scale`, but q/k/v come out of
+        # three GEMMs already contiguous ([N, h, d]) and the scale is folded into the q projection: no M- or N-sized
+        # permute / multiply passes around the pair ops
+        Wm, bm = self.qkv.weight, self.qkv.bias
+        query = torch.nn.functional.linear(feats, Wm[:C] * self.scale, None if bm is None else bm[:C] * self.scale).view(N, h, C // h)
+        key = torch.nn.functional.linear(feats, Wm[C:2 * C], None if bm is None else bm[C:2 * C]).view(N, h, C // h)
+        value = torch.nn.functional.linear(feats, Wm[2 * C:], None if bm is None else bm[2 * C:]).view(N, h, C // h)
         off, i1, rel = idx.index_0_offsets, idx.index_1, idx.rel_idx
         bias = None
         fused = self.rel_query and self.rel_key

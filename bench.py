@@ -250,12 +250,12 @@ def device_step(levels, grads_out, geo=None):
                        tv.data_ptr(), out.data_ptr(), stream)
             # backward
             gp = s                                      # reuse the M-sized buffer
-            gv = torch.zeros_like(v); gtv = torch.zeros_like(tv)
+            gv = torch.empty_like(v); gtv = torch.zeros_like(tv)
             _cabi.call("stb200_window_aggregate_backward", ctypes.byref(ix), h, HEAD_DIM, L, g.data_ptr(), p.data_ptr(),
                        v.data_ptr(), tv.data_ptr(), gp.data_ptr(), gv.data_ptr(), gtv.data_ptr(), stream)
             gs = torch.empty(M, h, device=dev)
             ext.segment_softmax_backward_cuda(N, M, h, p, gp, off, gs)
-            gq = torch.empty_like(q); gk = torch.zeros_like(k); gtq = torch.zeros_like(tq); gtk = torch.zeros_like(tk)
+            gq = torch.empty_like(q); gk = torch.empty_like(k); gtq = torch.zeros_like(tq); gtk = torch.zeros_like(tk)
             _cabi.call("stb200_window_logits_backward", ctypes.byref(ix), h, HEAD_DIM, L, gs.data_ptr(), q.data_ptr(),
                        k.data_ptr(), tq.data_ptr(), tk.data_ptr(), gq.data_ptr(), gk.data_ptr(), gtq.data_ptr(),
                        gtk.data_ptr(), stream)
@@ -410,7 +410,10 @@ def main():
             else:
                 cur, geo = upload(main), None
             model.zero_grad(set_to_none=True)
-            loss = model(cur["feat6"], cur["xyz"], cur["off"], cur["sub"], geo)
+            # the reference trains under AMP (config use_amp: True, train.py:336): Linear layers in reduced precision,
+            # the pair ops pinned to fp32 (custom_fwd cast_inputs, like the reference's .float() call sites)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                loss = model(cur["feat6"], cur["xyz"], cur["off"], cur["sub"], geo)
             loss.backward()
             if pf2 is not None:
                 pf2.complete()
@@ -430,7 +433,8 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": n_points * world / float(tt.item()), "unit": "points/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": 4, "ms_per_step": float(tt.item()) * 1e3, "steps": n_e2e,
-               "api": "WindowAttention modules (autograd) + build_layer_index, pinned host inputs"}
+               "api": "WindowAttention modules (autograd, bf16 autocast around the Linear layers as in the reference's AMP recipe; "
+                      "pair ops fp32) + index builder, pinned host inputs"}
 
     if rank != 0:
         if dist is not None:

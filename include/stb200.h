@@ -189,7 +189,9 @@ int stb200_rel_pos_index_swin(int N, const float *xyz, const int *index0_offsets
  * (:203); both gather the same key rows.  stb200_window_logits_* does q.k + rel-pos bias in one pass (and the matching
  * single-pass gradients); stb200_window_aggregate_* is attention_step2_with_rel_pos_value_v2 driven by the same index
  * descriptor.  rel_packed / t_rel_packed (optional, stb200_pack_rel) replace the 12-byte rel_idx rows by one 32-bit
- * word per pair (three 10-bit bins) in query-segment / key-segment order. */
+ * word per pair (three 10-bit bins) in query-segment / key-segment order.
+ * Output convention of the fused entry points: grad_q, grad_k, grad_v, grad_attn, logits, output are OVERWRITTEN (no
+ * zero-fill needed); only the table gradients are accumulated into (caller zero-fills them, they are a few KB). */
 typedef struct stb200_index {
     int N, M;
     const int *index0_offsets; /* [N+1] */

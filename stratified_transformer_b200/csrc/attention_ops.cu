@@ -978,10 +978,10 @@ int stb200_window_logits_backward(const stb200_index *ix, int h, int hdim, int L
     p.X = q; p.out = grad_table_q; p.row_order = nullptr;
     if (fold) { p.T2 = table_q; p.out2 = grad_q; }
     if (int rc = launch_table_grad<false>(hdim, p, M, "table_grad[logits_bwd_gtq]", s)) return rc;
-    // grad_k += sum over incoming pairs g * (q[i0] + Ek)                          (accumulated)
+    // grad_k = sum over incoming pairs g * (q[i0] + Ek)                           (overwritten)
     p.T2 = nullptr; p.out2 = nullptr; p.row_order = ix->row_order;
     p.packed = ix->t_rel_packed; p.offsets = ix->t_offsets; p.pair_id = ix->t_pair; p.gather_idx = ix->t_index0;
-    p.Y = q; p.Tx = table_k; p.out = grad_k; p.accumulate = 1;
+    p.Y = q; p.Tx = table_k; p.out = grad_k; p.accumulate = 0;   // fused API: grad_k is overwritten
     if (fold) {
         if (int rc = launch_seg_reduce<true, false, true>(hdim, p, M, "seg_reduce_t[logits_bwd_gk]", s)) return rc;
     } else {
@@ -1020,7 +1020,7 @@ int stb200_window_aggregate_backward(const stb200_index *ix, int h, int hdim, in
     p.w = attn; p.out = grad_table_v;
     if (int rc = launch_table_grad<false>(hdim, p, M, "table_grad[aggregate_bwd_gtv]", s)) return rc;
     p.packed = nullptr; p.Y = grad_out; p.offsets = ix->t_offsets; p.pair_id = ix->t_pair; p.gather_idx = ix->t_index0;
-    p.out = grad_v; p.accumulate = 1;
+    p.out = grad_v; p.accumulate = 0;   // fused API: grad_v is overwritten
     return launch_seg_reduce<true, false, true>(hdim, p, M, "seg_reduce_t[aggregate_bwd_gv]", s);
 }
 

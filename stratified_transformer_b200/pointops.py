@@ -215,7 +215,7 @@ class WindowLogits(Function):
         N, h, d = q.shape
         L = table_q.shape[0]
         grad_out = grad_out.contiguous()
-        gq, gk = torch.empty_like(q), torch.zeros_like(k)
+        gq, gk = torch.empty_like(q), torch.empty_like(k)
         gtq, gtk = torch.zeros_like(table_q), torch.zeros_like(table_k)
         _cabi.call("stb200_window_logits_backward", ctypes.byref(ctx.pair_index.c_struct(L, backward=True)), h, d, L,
                    grad_out.data_ptr(), q.data_ptr(), k.data_ptr(), table_q.data_ptr(), table_k.data_ptr(), gq.data_ptr(),
@@ -250,7 +250,7 @@ class WindowAggregate(Function):
         N, h, d = v.shape
         L = table_v.shape[0]
         grad_out = grad_out.contiguous()
-        ga, gv, gt = torch.empty_like(attn), torch.zeros_like(v), torch.zeros_like(table_v)
+        ga, gv, gt = torch.empty_like(attn), torch.empty_like(v), torch.zeros_like(table_v)
         _cabi.call("stb200_window_aggregate_backward", ctypes.byref(ctx.pair_index.c_struct(L, backward=True)), h, d, L,
                    grad_out.data_ptr(), attn.data_ptr(), v.data_ptr(), table_v.data_ptr(), ga.data_ptr(), gv.data_ptr(),
                    gt.data_ptr(), torch.cuda.current_stream().cuda_stream)

@@ -456,9 +456,15 @@ def main():
         top = max(attn, key=lambda k: attn[k]["ms"])
         tv = prof[top]
         ach = tv["bytes"] / (tv["ms"] * 1e-3) / 1e9
+        traffic = None
+        try:   # DRAM bytes per launch of this kernel from the committed ncu --set full capture (profiles/)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(top, {}).get("dram_bytes_per_launch")
+        except OSError:
+            pass
         roofline = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s",
-                    "traffic": None, "launches": tv["launches"], "avg_ms": tv["ms"] / tv["launches"],
+                    "traffic": traffic, "algorithmic_bytes_per_launch": tv["bytes"] / tv["launches"],
+                    "launches": tv["launches"], "avg_ms": tv["ms"] / tv["launches"],
                     "share_of_kernel_time": tv["ms"] / total_k,
                     "per_kernel_ms_per_step": {k: round(v / a.steps, 4) for k, v in sorted(kern_ms.items(), key=lambda kv: -kv[1])}}
 

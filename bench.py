@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="build the geometry serially inside the step instead of prefetching it on a side stream")
+    ap.add_argument("--fused", action="store_true", help="use the experimental fused per-window forward kernel in the device arm")
     ap.add_argument("--no-profile", action="store_true", help="do not bracket kernels with CUDA events in the timed region")
     ap.add_argument("--cpu-sample-points", type=int, default=0, help="points of the CPU sample scene (0 = auto)")
     return ap.parse_args()
@@ -223,7 +224,7 @@ def build_inputs(a, rank, dev):
     return levels, torch.from_numpy(rgb)
 
 
-def device_step(levels, grads_out, geo=None):
+def device_step(levels, grads_out, geo=None, no_fused=True):
     """One pass of the hot path with device-resident operands through the extension-level API (fused entry points:
     logits = q.k + rel-pos bias in one pass, segment softmax, aggregation; and their single-pass gradients)."""
     import ctypes
@@ -243,11 +244,23 @@ def device_step(levels, grads_out, geo=None):
             ix = pi.c_struct(L, backward=True)
             s = torch.empty(M, h, device=dev); p = torch.empty(M, h, device=dev)
             out = torch.empty(N, h, HEAD_DIM, device=dev)
-            _cabi.call("stb200_window_logits_forward", ctypes.byref(ix), h, HEAD_DIM, L, q.data_ptr(), k.data_ptr(),
-                       tq.data_ptr(), tk.data_ptr(), s.data_ptr(), stream)
-            ext.segment_softmax_forward_cuda(N, M, h, s, None, off, p)
-            _cabi.call("stb200_window_aggregate_forward", ctypes.byref(ix), h, HEAD_DIM, L, p.data_ptr(), v.data_ptr(),
-                       tv.data_ptr(), out.data_ptr(), stream)
+            plan = None if no_fused else pi.fused_plan()
+            rows = None
+            if plan is not None:      # per-window tensor-core kernel for the windows with one shared key list
+                flags, rows = plan
+                _cabi.call("stb200_window_attention_forward_fused", ctypes.byref(ix), pi.n_win, pi.win_offsets.data_ptr(),
+                           flags.data_ptr(), h, HEAD_DIM, L, q.data_ptr(), k.data_ptr(), v.data_ptr(), tq.data_ptr(), tk.data_ptr(),
+                           tv.data_ptr(), out.data_ptr(), p.data_ptr(), stream)
+            if plan is None or rows.numel() > 0:   # per-pair kernels on the remaining rows
+                ixf = pi.c_struct(L, backward=True)
+                if rows is not None:
+                    ixf.row_order, ixf.N = rows.data_ptr(), rows.numel()
+                _cabi.call("stb200_window_logits_forward", ctypes.byref(ixf), h, HEAD_DIM, L, q.data_ptr(), k.data_ptr(),
+                           tq.data_ptr(), tk.data_ptr(), s.data_ptr(), stream)
+                _cabi.call("stb200_segment_softmax_forward_rows", ixf.N, None if rows is None else rows.data_ptr(), h,
+                           s.data_ptr(), None, off.data_ptr(), p.data_ptr(), stream)
+                _cabi.call("stb200_window_aggregate_forward", ctypes.byref(ixf), h, HEAD_DIM, L, p.data_ptr(), v.data_ptr(),
+                           tv.data_ptr(), out.data_ptr(), stream)
             # backward
             gp = s                                      # reuse the M-sized buffer
             gv = torch.empty_like(v); gtv = torch.zeros_like(tv)
@@ -335,7 +348,7 @@ def main():
         if pf is not None:
             geo = pf.take()
             pf.submit(xyzs_d, offs_d, offs_h)
-        grads = device_step(levels, [], geo)
+        grads = device_step(levels, [], geo, not a.fused)
         if pf is not None:
             pf.complete()
         if dist is not None:   # training only: data-parallel gradient all-reduce of the attention parameters

@@ -157,8 +157,8 @@ int stb200_furthestsampling(int b, int n, const float *xyz, const int *offset, c
  *
  *   1. stb200_stratified_pairs_count: window partition for one block parity (0: unshifted, 1: shifted by
  *      w/2), sampled keys from `downsample_idx` (m = 0 -> dense pairs only, the Swin variant), per-query
- *      key counts -> index0_offsets [N+1] and totals[4] = {M, n_max, error flag, 0} (device memory).
- *      Intermediate state stays in `workspace` (stb200_pair_builder_workspace_bytes(N) bytes).
+ *      key counts -> index0_offsets [N+1] and totals[4] = {M, n_max, error flag, n_windows} (device memory).
+ *      totals[3] = number of small windows.  Intermediate state stays in `workspace` (stb200_pair_builder_workspace_bytes(N) bytes).
  *   2. stb200_stratified_pairs_fill: emits index_1 [M] (per query: dense keys ascending by point id, then
  *      sparse keys ascending by point id), rel_idx [M,3] (may be NULL) and index_0 [M] (may be NULL) from the
  *      same workspace.  window_size_x2 = (float)(2.0 * window_size), quant_size as fp32 — the scalars of
@@ -171,6 +171,7 @@ int stb200_stratified_pairs_count(int N, int b, const float *xyz, const int *off
 int stb200_stratified_pairs_fill(int N, const float *xyz, float window_size_x2, float quant_size, int has_sparse,
                                  void *workspace, size_t workspace_bytes, const int *index0_offsets, int *index_1,
                                  int *rel_idx, int *index_0, int *row_order /* [N] points sorted by window, may be NULL */,
+                                 int *win_offsets /* [n_win+1] window boundaries in row_order, may be NULL */, int n_win,
                                  int M, void *stream);
 
 /* Relative-position index of an existing CSR pair list.
@@ -218,6 +219,24 @@ int stb200_window_aggregate_forward(const stb200_index *ix, int h, int hdim, int
 int stb200_window_aggregate_backward(const stb200_index *ix, int h, int hdim, int L, const float *grad_out,
                                      const float *attn, const float *v, const float *table_v, float *grad_attn,
                                      float *grad_v, float *grad_table_v, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused window-attention forward: logits + rel-pos bias + softmax + aggregation per window on the
+ * tensor cores, no M-sized intermediate besides the probabilities `attn` [M,h] that the backward pass consumes.
+ * stb200_classify_windows marks the windows whose queries all share one key list of at most stb200_fused_max_keys()
+ * keys (flags[w] = 1) and lists the rows of all other windows (fallback_rows[0..*fallback_count)); the caller runs
+ * the per-pair entry points on those rows (stb200_index.row_order = fallback_rows, N = count).  Requires
+ * rel_packed, row_order (points sorted by window) and win_offsets from the pair builder; head dim 16, L <= 85. */
+int stb200_fused_max_keys(void);
+int stb200_classify_windows(int n_win, const int *win_offsets, const int *row_order, const int *index0_offsets,
+                            const int *index1, unsigned char *flags, int *fallback_rows, int *fallback_count, void *stream);
+int stb200_window_attention_forward_fused(const stb200_index *ix, int n_win, const int *win_offsets,
+                                          const unsigned char *win_flags, int h, int hdim, int L, const float *q,
+                                          const float *k, const float *v, const float *table_q, const float *table_k,
+                                          const float *table_v, float *output, float *attn, void *stream);
+/* segment softmax restricted to a list of rows (rows = NULL: all N rows) */
+int stb200_segment_softmax_forward_rows(int n_rows, const int *rows, int h, const float *a, const float *b,
+                                        const int *index0_offsets, float *p, void *stream);
 
 #ifdef __cplusplus
 }

@@ -45,13 +45,16 @@ _SIGNATURES = {
     "stb200_attention_step2_with_rel_pos_value_backward": [_c_int] * 5 + [P] * 11,
     "stb200_furthestsampling": [_c_int, _c_int] + [P] * 6,
     "stb200_stratified_pairs_count": [_c_int, _c_int, P, P, ctypes.c_float, _c_int, P, _c_int, P, _c_size_t, P, P, P],
-    "stb200_stratified_pairs_fill": [_c_int, P, ctypes.c_float, ctypes.c_float, _c_int, P, _c_size_t, P, P, P, P, P, _c_int, P],
+    "stb200_stratified_pairs_fill": [_c_int, P, ctypes.c_float, ctypes.c_float, _c_int, P, _c_size_t, P, P, P, P, P, P, _c_int, _c_int, P],
     "stb200_rel_pos_index_stratified": [_c_int, P, P, P, ctypes.c_float, ctypes.c_float, P, P],
     "stb200_pack_rel": [_c_int, _c_int, P, P, P, P],
     "stb200_window_logits_forward": [_IX, _c_int, _c_int, _c_int] + [P] * 6,
     "stb200_window_logits_backward": [_IX, _c_int, _c_int, _c_int] + [P] * 10,
     "stb200_window_aggregate_forward": [_IX, _c_int, _c_int, _c_int] + [P] * 5,
     "stb200_window_aggregate_backward": [_IX, _c_int, _c_int, _c_int] + [P] * 8,
+    "stb200_classify_windows": [_c_int, P, P, P, P, P, P, P, P],
+    "stb200_window_attention_forward_fused": [_IX, _c_int, P, P, _c_int, _c_int, _c_int] + [P] * 9,
+    "stb200_segment_softmax_forward_rows": [_c_int, P, _c_int, P, P, P, P, P],
     "stb200_rel_pos_index_swin": [_c_int, P, P, P, ctypes.c_float, ctypes.c_float, ctypes.c_float, _c_int, P, P, P, P],
 }
 _RESTYPES = {
@@ -60,6 +63,7 @@ _RESTYPES = {
     "stb200_version": (_c_int, []),
     "stb200_transpose_csr_workspace_bytes": (_c_size_t, [_c_int, _c_int]),
     "stb200_pair_builder_workspace_bytes": (_c_size_t, [_c_int]),
+    "stb200_fused_max_keys": (_c_int, []),
     "stb200_profile_enable": (None, [_c_int]),
     "stb200_profile_dump": (_c_size_t, [ctypes.c_char_p, _c_size_t]),
 }

@@ -535,12 +535,14 @@ template <int HP>
 __global__ void __launch_bounds__(kThreads) segment_softmax_fwd_hp_kernel(int N, int h, const float *__restrict__ a,
                                                                           const float *__restrict__ b,
                                                                           const int *__restrict__ offsets,
-                                                                          float *__restrict__ p) {
+                                                                          float *__restrict__ p,
+                                                                          const int *__restrict__ rows = nullptr) {
     constexpr int SL = kWarp / HP;
     const int lane = threadIdx.x % kWarp, hd = lane % HP, slot = lane / HP;
     const bool on = hd < h;
     const int wid = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp, nw = gridDim.x * blockDim.x / kWarp;
-    for (int n = wid; n < N; n += nw) {
+    for (int nn = wid; nn < N; nn += nw) {
+        const int n = rows ? __ldg(rows + nn) : nn;
         const int start = __ldg(offsets + n), len = __ldg(offsets + n + 1) - start;
         if (len <= 0) continue;
         const size_t base = (size_t)start * h + hd;
@@ -906,6 +908,25 @@ int stb200_segment_softmax_forward(int N, int M, int h, const float *a, const fl
         else segment_softmax_fwd_kernel<<<blocks, kThreads, 0, s>>>(N, h, a, b, index0_offsets, p);
     }
     return check_launch("segment_softmax_fwd");
+}
+
+int stb200_segment_softmax_forward_rows(int n_rows, const int *rows, int h, const float *a, const float *b,
+                                        const int *index0_offsets, float *p, void *stream) {
+    STB200_REQUIRE(n_rows >= 0 && h > 0 && h <= 32, STB200_ERR_ARG, "bad sizes (h <= 32)");
+    if (n_rows == 0) return STB200_OK;
+    STB200_REQUIRE(a && index0_offsets && p, STB200_ERR_ARG, "null pointer");
+    const int blocks = max(1, min((n_rows + kThreads / kWarp - 1) / (kThreads / kWarp), kNumSMs * 8));
+    cudaStream_t s = (cudaStream_t)stream;
+    {
+        KernelScope ks("segment_softmax_fwd", 0.0, s);
+        if (h <= 1) segment_softmax_fwd_hp_kernel<1><<<blocks, kThreads, 0, s>>>(n_rows, h, a, b, index0_offsets, p, rows);
+        else if (h <= 2) segment_softmax_fwd_hp_kernel<2><<<blocks, kThreads, 0, s>>>(n_rows, h, a, b, index0_offsets, p, rows);
+        else if (h <= 4) segment_softmax_fwd_hp_kernel<4><<<blocks, kThreads, 0, s>>>(n_rows, h, a, b, index0_offsets, p, rows);
+        else if (h <= 8) segment_softmax_fwd_hp_kernel<8><<<blocks, kThreads, 0, s>>>(n_rows, h, a, b, index0_offsets, p, rows);
+        else if (h <= 16) segment_softmax_fwd_hp_kernel<16><<<blocks, kThreads, 0, s>>>(n_rows, h, a, b, index0_offsets, p, rows);
+        else segment_softmax_fwd_hp_kernel<32><<<blocks, kThreads, 0, s>>>(n_rows, h, a, b, index0_offsets, p, rows);
+    }
+    return check_launch("segment_softmax_fwd_rows");
 }
 
 int stb200_segment_softmax_backward(int N, int M, int h, const float *p, const float *grad_p,

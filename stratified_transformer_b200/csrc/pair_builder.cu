@@ -275,13 +275,13 @@ __global__ void count_pairs_kernel(int N, const int *__restrict__ win_s, const i
     }
 }
 
-__global__ void finish_count_kernel(int N, const int *__restrict__ offsets, GridParams *gp, int *totals) {
+__global__ void finish_count_kernel(int N, const int *__restrict__ offsets, const int *__restrict__ rank_s, GridParams *gp, int *totals) {
     if (threadIdx.x || blockIdx.x) return;
     gp->M = offsets[N];
     totals[0] = offsets[N];
     totals[1] = gp->n_max;
     totals[2] = gp->err;
-    totals[3] = 0;
+    totals[3] = rank_s[N - 1];   // number of small windows
 }
 
 // one warp per query: emit keys (dense ascending id, then sparse ascending id) + rel-pos index (+ index_0)
@@ -425,13 +425,13 @@ int stb200_stratified_pairs_count(int N, int b, const float *xyz, const int *off
                                                                        has_sparse);
     tb = st.cub_bytes;
     cub::DeviceScan::ExclusiveSum(st.cub_tmp, tb, st.counts, index0_offsets, N + 1, s);
-    finish_count_kernel<<<1, 32, 0, s>>>(N, index0_offsets, st.gp, totals);
+    finish_count_kernel<<<1, 32, 0, s>>>(N, index0_offsets, st.rank_s, st.gp, totals);
     return check_launch("stratified_pairs_count");
 }
 
 int stb200_stratified_pairs_fill(int N, const float *xyz, float window_size_x2, float quant_size, int has_sparse,
                                  void *workspace, size_t workspace_bytes, const int *index0_offsets, int *index_1,
-                                 int *rel_idx, int *index_0, int *row_order, int M, void *stream) {
+                                 int *rel_idx, int *index_0, int *row_order, int *win_offsets, int n_win, int M, void *stream) {
     STB200_REQUIRE(N > 0 && xyz && workspace && index0_offsets && index_1, STB200_ERR_ARG, "null pointer / bad N");
     STB200_REQUIRE(workspace_bytes >= stb200_pair_builder_workspace_bytes(N), STB200_ERR_WORKSPACE, "workspace too small");
     BuilderState st;
@@ -445,6 +445,8 @@ int stb200_stratified_pairs_fill(int N, const float *xyz, float window_size_x2, 
             has_sparse, window_size_x2, quant_size, index_1, rel_idx, index_0);
     }
     if (row_order) cudaMemcpyAsync(row_order, st.order_s, (size_t)N * sizeof(int), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    if (win_offsets && n_win > 0)
+        cudaMemcpyAsync(win_offsets, st.wstart_s, (size_t)(n_win + 1) * sizeof(int), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
     return check_launch("stratified_pairs_fill");
 }
 

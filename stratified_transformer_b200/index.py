@@ -32,6 +32,9 @@ class PairIndex:
     M: int
     index_0: torch.Tensor | None = None    # [M]   only when asked for (v1 ops, scatter_softmax callers)
     row_order: torch.Tensor | None = None  # [N]   points sorted by window (locality hint for the fused entry points)
+    win_offsets: torch.Tensor | None = None  # [n_win+1] window boundaries inside row_order
+    n_win: int = 0
+    _fused: tuple | None = field(default=None, repr=False)   # (flags u8 [n_win], fallback_rows i32 [count])
     _tcsr: ext.TransposedCSR | None = field(default=None, repr=False)
     _packed: dict = field(default_factory=dict, repr=False)   # L -> (rel_packed, t_rel_packed | None)
 
@@ -45,6 +48,22 @@ class PairIndex:
         if self._tcsr is None:
             self._tcsr = ext.build_transposed_csr(self.index_0_offsets, self.index_1)
         return self._tcsr
+
+    def fused_plan(self):
+        """(window flags, fallback row list) for the fused forward kernel: which windows have one shared key list that
+        fits its tile, and the rows of all the others.  Computed once per pair list (one small host read)."""
+        if self._fused is None:
+            if self.row_order is None or self.win_offsets is None or self.n_win == 0:
+                return None
+            dev = self.index_1.device
+            flags = torch.empty(self.n_win, dtype=torch.uint8, device=dev)
+            rows = torch.empty(self.N, dtype=torch.int32, device=dev)
+            count = torch.zeros(1, dtype=torch.int32, device=dev)
+            _cabi.call("stb200_classify_windows", self.n_win, self.win_offsets.data_ptr(), self.row_order.data_ptr(),
+                       self.index_0_offsets.data_ptr(), self.index_1.data_ptr(), flags.data_ptr(), rows.data_ptr(),
+                       count.data_ptr(), _stream())
+            self._fused = (flags, rows[:int(count.item())].contiguous())
+        return self._fused
 
     def _pack(self, L: int, perm):
         out = torch.empty(self.M, dtype=torch.int32, device=self.index_1.device)
@@ -100,20 +119,22 @@ def build_stratified_index(xyz: torch.Tensor, offset: torch.Tensor, window_size:
     _cabi.call("stb200_stratified_pairs_count", N, b, xyz.data_ptr(), offset.data_ptr(), float(window_size),
                int(parity) & 1, ds_ptr, m, workspace.data_ptr(), workspace.numel(), offsets.data_ptr(),
                totals.data_ptr(), _stream())
-    M, n_max, err, _ = totals.tolist()      # the one host sync: the caller has to allocate M-sized outputs
+    M, n_max, err, n_win = totals.tolist()      # the one host sync: the caller has to allocate M-sized outputs
     if err:
         raise _cabi.Stb200Error("pair builder: window grid has more than 2^32 cells (window too small for the scene extent)")
     index_1 = torch.empty(M, dtype=torch.int32, device=dev)
     rel_idx = torch.empty(M, 3, dtype=torch.int32, device=dev) if quant_size is not None else None
     index_0 = torch.empty(M, dtype=torch.int32, device=dev) if want_index_0 else None
     row_order = torch.empty(N, dtype=torch.int32, device=dev)
+    win_offsets = torch.empty(n_win + 1, dtype=torch.int32, device=dev)
     if M:
         _cabi.call("stb200_stratified_pairs_fill", N, xyz.data_ptr(), float(2 * window_size),
                    float(quant_size if quant_size is not None else 1.0), int(m > 0), workspace.data_ptr(),
                    workspace.numel(), offsets.data_ptr(), index_1.data_ptr(),
                    None if rel_idx is None else rel_idx.data_ptr(), None if index_0 is None else index_0.data_ptr(),
-                   row_order.data_ptr(), M, _stream())
-    return PairIndex(offsets, index_1, rel_idx, int(n_max), int(M), index_0, row_order if M else None)
+                   row_order.data_ptr(), win_offsets.data_ptr(), n_win, M, _stream())
+    return PairIndex(offsets, index_1, rel_idx, int(n_max), int(M), index_0, row_order if M else None,
+                     win_offsets if M else None, int(n_win) if M else 0)
 
 
 def rel_pos_index_stratified(xyz, index_0_offsets, index_1, window_size: float, quant_size: float) -> torch.Tensor:
@@ -209,21 +230,24 @@ class PendingLayerIndex:
         dev = self.xyz.device
         built = []
         for ws, offsets, totals, host in self.parts:
-            M, n_max, err, _ = host.tolist()
+            M, n_max, err, n_win = host.tolist()
             if err:
                 raise _cabi.Stb200Error("pair builder: window grid has more than 2^32 cells")
             index_1 = torch.empty(M, dtype=torch.int32, device=dev)
             rel_idx = torch.empty(M, 3, dtype=torch.int32, device=dev)
             index_0 = torch.empty(M, dtype=torch.int32, device=dev) if self.want_index_0 else None
             row_order = torch.empty(self.N, dtype=torch.int32, device=dev)
+            win_offsets = torch.empty(n_win + 1, dtype=torch.int32, device=dev)
             if M:
                 _cabi.call("stb200_stratified_pairs_fill", self.N, self.xyz.data_ptr(), float(2 * self.window_size),
                            float(self.quant_size), int(self.m > 0), ws.data_ptr(), ws.numel(), offsets.data_ptr(),
                            index_1.data_ptr(), rel_idx.data_ptr(), None if index_0 is None else index_0.data_ptr(),
-                           row_order.data_ptr(), M, _stream())
-            pi = PairIndex(offsets, index_1, rel_idx, int(n_max), int(M), index_0, row_order if M else None)
+                           row_order.data_ptr(), win_offsets.data_ptr(), n_win, M, _stream())
+            pi = PairIndex(offsets, index_1, rel_idx, int(n_max), int(M), index_0, row_order if M else None,
+                           win_offsets if M else None, int(n_win) if M else 0)
             if self.L is not None:
                 pi.c_struct(self.L, backward=True)   # transposed CSR + packed bins, eagerly, on this stream
+                pi.fused_plan()
             built.append(pi)
         self.parts = None
         li = LayerIndex(self.ds_idx, tuple(built))
@@ -234,7 +258,9 @@ class PendingLayerIndex:
 def record_stream(li: "LayerIndex", stream) -> None:
     """Tell the caching allocator that `stream` consumes the index tensors (they were allocated on another stream)."""
     for pi in li.parity:
-        ts = [pi.index_0_offsets, pi.index_1, pi.rel_idx, pi.index_0, pi.row_order]
+        ts = [pi.index_0_offsets, pi.index_1, pi.rel_idx, pi.index_0, pi.row_order, pi.win_offsets]
+        if pi._fused is not None:
+            ts += list(pi._fused)
         if pi._tcsr is not None:
             ts += [pi._tcsr.t_offsets, pi._tcsr.t_pair, pi._tcsr.t_index0]
         for a, b in pi._packed.values():

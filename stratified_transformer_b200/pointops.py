@@ -261,6 +261,73 @@ def window_aggregate(attn, v, table_v, pair_index):
     return WindowAggregate.apply(attn, v, table_v, pair_index)
 
 
+class WindowAttentionFused(Function):
+    """Whole pair path of WindowAttention.forward in one kernel per window tile:
+    softmax_seg(q.k + rel-pos bias) applied to (v + rel-pos value), tensor-core table products, no M-sized
+    intermediate except the probabilities kept for backward.  Windows the fused kernel cannot take (queries with
+    differing key lists, or more than stb200_fused_max_keys() keys) go through the per-pair entry points on the
+    complementary row list.  Backward = the single-pass gradient kernels of window_aggregate / segment_softmax /
+    window_logits."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, q, k, v, table_q, table_k, table_v, pair_index):
+        _contig(q, k, v, table_q, table_k, table_v)
+        N, h, d = q.shape
+        L = table_q.shape[0]
+        plan = pair_index.fused_plan() if (d == 16 and 3 * L <= 256) else None
+        stream = torch.cuda.current_stream().cuda_stream
+        M = pair_index.M
+        out = torch.empty(N, h, d, dtype=torch.float32, device=q.device)
+        p = torch.empty(M, h, dtype=torch.float32, device=q.device)
+        ix = pair_index.c_struct(L)
+        rows = None
+        if plan is not None:
+            flags, rows = plan
+            _cabi.call("stb200_window_attention_forward_fused", ctypes.byref(ix), pair_index.n_win,
+                       pair_index.win_offsets.data_ptr(), flags.data_ptr(), h, d, L, q.data_ptr(), k.data_ptr(), v.data_ptr(),
+                       table_q.data_ptr(), table_k.data_ptr(), table_v.data_ptr(), out.data_ptr(), p.data_ptr(), stream)
+        if plan is None or rows.numel() > 0:
+            # per-pair kernels on the rows the fused kernel skipped (all rows when it is not applicable)
+            if rows is not None:
+                ix.row_order, ix.N = rows.data_ptr(), rows.numel()
+            s = torch.empty(M, h, dtype=torch.float32, device=q.device)
+            _cabi.call("stb200_window_logits_forward", ctypes.byref(ix), h, d, L, q.data_ptr(), k.data_ptr(),
+                       table_q.data_ptr(), table_k.data_ptr(), s.data_ptr(), stream)
+            _cabi.call("stb200_segment_softmax_forward_rows", ix.N, None if rows is None else rows.data_ptr(), h, s.data_ptr(),
+                       None, pair_index.index_0_offsets.data_ptr(), p.data_ptr(), stream)
+            _cabi.call("stb200_window_aggregate_forward", ctypes.byref(ix), h, d, L, p.data_ptr(), v.data_ptr(),
+                       table_v.data_ptr(), out.data_ptr(), stream)
+        ctx.save_for_backward(q, k, v, table_q, table_k, table_v, p)
+        ctx.pair_index = pair_index
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, grad_out):
+        q, k, v, table_q, table_k, table_v, p = ctx.saved_tensors
+        pi = ctx.pair_index
+        N, h, d = q.shape
+        L = table_q.shape[0]
+        stream = torch.cuda.current_stream().cuda_stream
+        grad_out = grad_out.contiguous()
+        ix = pi.c_struct(L, backward=True)
+        gp, gv, gtv = torch.empty_like(p), torch.empty_like(v), torch.zeros_like(table_v)
+        _cabi.call("stb200_window_aggregate_backward", ctypes.byref(ix), h, d, L, grad_out.data_ptr(), p.data_ptr(), v.data_ptr(),
+                   table_v.data_ptr(), gp.data_ptr(), gv.data_ptr(), gtv.data_ptr(), stream)
+        gs = torch.empty_like(p)
+        pointops_cuda.segment_softmax_backward_cuda(N, pi.M, h, p, gp, pi.index_0_offsets, gs)
+        gq, gk = torch.empty_like(q), torch.empty_like(k)
+        gtq, gtk = torch.zeros_like(table_q), torch.zeros_like(table_k)
+        _cabi.call("stb200_window_logits_backward", ctypes.byref(ix), h, d, L, gs.data_ptr(), q.data_ptr(), k.data_ptr(),
+                   table_q.data_ptr(), table_k.data_ptr(), gq.data_ptr(), gk.data_ptr(), gtq.data_ptr(), gtk.data_ptr(), stream)
+        return gq, gk, gv, gtq, gtk, gtv, None
+
+
+def window_attention_fused(q, k, v, table_q, table_k, table_v, pair_index):
+    return WindowAttentionFused.apply(q, k, v, table_q, table_k, table_v, pair_index)
+
+
 def segment_softmax(a, index0_offsets, b=None):
     return SegmentSoftmax.apply(a, b, index0_offsets)
 

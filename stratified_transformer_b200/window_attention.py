@@ -70,6 +70,16 @@ class WindowAttention(nn.Module):
         key = torch.nn.functional.linear(feats, Wm[C:2 * C], None if bm is None else bm[C:2 * C]).view(N, h, C // h)
         value = torch.nn.functional.linear(feats, Wm[2 * C:], None if bm is None else bm[2 * C:]).view(N, h, C // h)
         off, i1, rel = idx.index_0_offsets, idx.index_1, idx.rel_idx
+        if getattr(self, "fused_forward", False) and self.rel_query and self.rel_key and self.rel_value:
+            # opt-in (module.fused_forward = True): whole pair path in one op, per-window tensor-core kernel where the
+            # window structure allows it.  First version, currently slower than the per-pair kernels.
+            x = pointops.window_attention_fused(query.float(), key.float(), value.float(),
+                                                self.relative_pos_query_table.float(), self.relative_pos_key_table.float(),
+                                                self.relative_pos_value_table.float(), idx)
+            x = x.view(N, C)
+            if not torch.is_autocast_enabled():
+                x = x.to(self.proj.weight.dtype)
+            return self.proj_drop(self.proj(x))
         bias = None
         fused = self.rel_query and self.rel_key
         if fused:   # q.k + rel-pos bias in one pass over the pairs

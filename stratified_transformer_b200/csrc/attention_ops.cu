@@ -29,6 +29,7 @@
 namespace stb200 {
 
 constexpr int kThreads = 256;
+constexpr int kMaxSegThreads = 512;   // seg_dot / seg_reduce may run with 256 or 512 threads per CTA (same staged tables, more warps)
 constexpr int kRowsPerChunk = 64;  // rows (queries or keys) a CTA takes per grid-stride step
 
 struct SegParams {
@@ -90,7 +91,7 @@ __device__ __forceinline__ float4 table_sum4(const float *ts, int L, int r0, int
 //   step2-rpv bwd gattn  XY|EX        x=grad_out[n] y=v[i1]      Tx=table_v
 // A warp owns a query; its len*HG (pair, head) items are spread over 32/G lane groups of G=D/4 lanes.
 template <int D, int HG, bool XY, bool EX, bool EY>
-__global__ void __launch_bounds__(kThreads) seg_dot_kernel(const SegParams p) {
+__global__ void __launch_bounds__(kMaxSegThreads) seg_dot_kernel(const SegParams p) {
     extern __shared__ float4 smem4[];
     float *smem = reinterpret_cast<float *>(smem4);
     constexpr int G = D / 4, NS = kWarp / G;
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(kThreads) seg_dot_kernel(const SegParams p) {
 //   step2 bwd grad_v     HAS_Y  PERM   w=attn  Y=grad_out by t_index0
 // A warp owns a row; 32/G pair slots of G lanes each accumulate float4 per head, then xor-shuffle across slots.
 template <int D, int HG, bool HAS_Y, bool HAS_T, bool PERM>
-__global__ void __launch_bounds__(kThreads) seg_reduce_kernel(const SegParams p) {
+__global__ void __launch_bounds__(kMaxSegThreads) seg_reduce_kernel(const SegParams p) {
     extern __shared__ float4 smem4[];
     float *ts = reinterpret_cast<float *>(smem4);
     constexpr int G = D / 4, NS = kWarp / G;
@@ -633,6 +634,13 @@ __global__ void __launch_bounds__(kThreads) segment_softmax_bwd_hp_kernel(int N,
 
 // ------------------------------------------------------------------------------------------------
 // host-side launch helpers
+// threads per CTA of the segment kernels: tuning knob STB200_SEG_THREADS (256 / 512), default by table use
+static int seg_threads(int ntables) {
+    static const int env = getenv("STB200_SEG_THREADS") ? atoi(getenv("STB200_SEG_THREADS")) : 0;
+    if (env == 256 || env == 512) return env;
+    return ntables > 0 ? 512 : kThreads;   // table variants are shared-memory / latency bound: more warps per staged table copy
+}
+
 static int grid_rows(int N, size_t smem, int groups) {
     const int chunks = (N + kRowsPerChunk - 1) / kRowsPerChunk;
     const int ctas_per_sm = (int)max((size_t)1, min((size_t)4, (size_t)(220 * 1024) / max(smem, (size_t)1)));
@@ -679,13 +687,14 @@ static double seg_bytes(const SegParams &p, int D, int M, bool rows_x, bool rows
 
 template <int D, int HG, bool XY, bool EX, bool EY>
 static int launch_seg_dot_hg(const SegParams &p, int M, const char *name, cudaStream_t s) {
-    const size_t smem = ((size_t)(EX + EY) * 3 * p.L * HG * D + (kThreads / kWarp) * HG * D) * sizeof(float);
+    const int threads = seg_threads(EX + EY);
+    const size_t smem = ((size_t)(EX + EY) * 3 * p.L * HG * D + (threads / kWarp) * HG * D) * sizeof(float);
     auto kern = seg_dot_kernel<D, HG, XY, EX, EY>;
     if (int rc = prep_smem(kern, smem)) return rc;
     dim3 grid(grid_rows(p.N, smem, p.h / HG), p.h / HG);
     {
         KernelScope ks(name, seg_bytes(p, D, M, true, true, false, true, false, EX + EY, true), s);
-        kern<<<grid, kThreads, smem, s>>>(p);
+        kern<<<grid, threads, smem, s>>>(p);
     }
     return check_launch(name);
 }
@@ -715,7 +724,7 @@ static int launch_seg_reduce_hg(const SegParams &p, int M, const char *name, cud
     dim3 grid(grid_rows(p.N, smem, p.h / HG), p.h / HG);
     {
         KernelScope ks(name, seg_bytes(p, D, M, false, HAS_Y, true, HAS_Y, PERM, HAS_T, false), s);
-        kern<<<grid, kThreads, smem, s>>>(p);
+        kern<<<grid, seg_threads(HAS_T && !PERM), smem, s>>>(p);
     }
     return check_launch(name);
 }

@@ -238,6 +238,14 @@ int stb200_window_attention_forward_fused(const stb200_index *ix, int n_win, con
 int stb200_segment_softmax_forward_rows(int n_rows, const int *rows, int h, const float *a, const float *b,
                                         const int *index0_offsets, float *p, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * k nearest neighbours per scene — replaces knnquery_cuda_launcher
+ * (knnquery/knnquery_cuda_kernel.h).  `b` = number of scenes (the reference walks new_offset until it finds the
+ * query's scene).  idx [m, nsample] int32 ascending by squared distance, dist2 [m, nsample] squared distances;
+ * identical to the reference including the order of equal distances.  nsample <= 100 (the reference's heap size). */
+int stb200_knnquery(int m, int b, int nsample, const float *xyz, const float *new_xyz, const int *offset,
+                    const int *new_offset, int *idx, float *dist2, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

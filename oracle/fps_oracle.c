@@ -66,3 +66,44 @@ void fps_oracle(int b, int n_max, const float *xyz, const int *offset, const int
     free(dists);
     free(dists_i);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * kNN oracle: literal restatement of /root/reference/lib/pointops2/src/knnquery/knnquery_cuda_kernel.cu:21-108
+ * (per query: scan the scene in index order, binary max-heap of k, heap sort), distance contracted like the SASS
+ * of the reference build: fma(dz,dz, fma(dx,dx, dy*dy)).  Pinned on the GPU against the reference kernel itself
+ * (tests/test_gpu_knn.py). */
+static void knn_reheap(float *dist, int *idx, int k) {
+    int root = 0, child = 1;
+    while (child < k) {
+        if (child + 1 < k && dist[child + 1] > dist[child]) child++;
+        if (dist[root] > dist[child]) return;
+        float td = dist[root]; dist[root] = dist[child]; dist[child] = td;
+        int ti = idx[root]; idx[root] = idx[child]; idx[child] = ti;
+        root = child;
+        child = root * 2 + 1;
+    }
+}
+
+void knn_oracle(int m, int b, int k, const float *xyz, const float *new_xyz, const int *offset, const int *new_offset,
+                int *idx, float *dist2) {
+    float bd[100];
+    int bi[100];
+    for (int q = 0; q < m; ++q) {
+        int s = 0;
+        while (s < b - 1 && q >= new_offset[s]) ++s;
+        const int start = s ? offset[s - 1] : 0, end = offset[s];
+        const float nx = new_xyz[q * 3], ny = new_xyz[q * 3 + 1], nz = new_xyz[q * 3 + 2];
+        for (int i = 0; i < k; ++i) { bd[i] = 1e10f; bi[i] = start; }
+        for (int i = start; i < end; ++i) {
+            const float dx = nx - xyz[i * 3], dy = ny - xyz[i * 3 + 1], dz = nz - xyz[i * 3 + 2];
+            const float d2 = fmaf(dz, dz, fmaf(dx, dx, dy * dy));
+            if (d2 < bd[0]) { bd[0] = d2; bi[0] = i; knn_reheap(bd, bi, k); }
+        }
+        for (int i = k - 1; i > 0; --i) {
+            float td = bd[0]; bd[0] = bd[i]; bd[i] = td;
+            int ti = bi[0]; bi[0] = bi[i]; bi[i] = ti;
+            knn_reheap(bd, bi, i);
+        }
+        for (int i = 0; i < k; ++i) { idx[q * k + i] = bi[i]; dist2[q * k + i] = bd[i]; }
+    }
+}

@@ -42,3 +42,20 @@ def furthestsampling(xyz, offset, new_offset):
     _load().fps_oracle(offset.shape[0], int(sizes.max()), xyz.ctypes.data, offset.ctypes.data,
                        new_offset.ctypes.data, tmp.ctypes.data, idx.ctypes.data)
     return idx
+
+
+def knnquery(nsample, xyz, new_xyz, offset, new_offset):
+    """-> (idx int32 [m,nsample], dist2 float32 [m,nsample]) exactly as the reference kernel produces them."""
+    lib = _load()
+    lib.knn_oracle.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p] * 6
+    lib.knn_oracle.restype = None
+    xyz = np.ascontiguousarray(xyz, np.float32)
+    new_xyz = np.ascontiguousarray(new_xyz, np.float32)
+    offset = np.ascontiguousarray(offset, np.int32)
+    new_offset = np.ascontiguousarray(new_offset, np.int32)
+    m = new_xyz.shape[0]
+    idx = np.zeros((m, nsample), np.int32)
+    d2 = np.zeros((m, nsample), np.float32)
+    lib.knn_oracle(m, offset.shape[0], nsample, xyz.ctypes.data, new_xyz.ctypes.data, offset.ctypes.data,
+                   new_offset.ctypes.data, idx.ctypes.data, d2.ctypes.data)
+    return idx, d2

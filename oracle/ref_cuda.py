@@ -145,3 +145,11 @@ def furthestsampling(xyz, offset, new_offset):
     tmp = torch.full((xyz.shape[0],), 1e10, device=xyz.device)
     _call("furthestsampling_cuda_launcher", b, n_max, _p(xyz), _p(offset), _p(new_offset), _p(tmp), _p(idx))
     return idx
+
+
+def knnquery(nsample, xyz, new_xyz, offset, new_offset):
+    m = new_xyz.shape[0]
+    idx = torch.zeros(m, nsample, dtype=torch.int32, device=xyz.device)
+    d2 = torch.zeros(m, nsample, device=xyz.device)
+    _call("knnquery_cuda_launcher", m, nsample, _p(xyz), _p(new_xyz), _p(offset), _p(new_offset), _p(idx), _p(d2))
+    return idx, d2

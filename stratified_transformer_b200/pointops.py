@@ -482,3 +482,55 @@ class AttentionStep2WithRelPosValue(Function):
 
 
 attention_step2_with_rel_pos_value = AttentionStep2WithRelPosValue.apply
+
+
+# ------------------------------------------------------------------------------------------------ neighbourhood ops
+# (what TransitionDown / Upsample call, model/stratified_transformer.py:103-106, 341)
+class KNNQuery(Function):
+    @staticmethod
+    def forward(ctx, nsample, xyz, new_xyz, offset, new_offset):
+        """xyz (n,3), new_xyz (m,3) or None, offset (b), new_offset (b) -> idx (m,nsample) i32, dist (m,nsample) f32
+        (Euclidean distance, i.e. sqrt of the kernel's squared distance: pointops.py:34-49)."""
+        if new_xyz is None:
+            new_xyz = xyz
+        _contig(xyz, new_xyz)
+        m = new_xyz.shape[0]
+        idx = torch.empty(m, nsample, dtype=torch.int32, device=xyz.device)
+        dist2 = torch.empty(m, nsample, dtype=torch.float32, device=xyz.device)
+        pointops_cuda.knnquery_cuda(m, nsample, xyz, new_xyz, offset.int().contiguous(), new_offset.int().contiguous(), idx, dist2)
+        ctx.mark_non_differentiable(idx)
+        return idx, torch.sqrt(dist2)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        return None, None, None, None, None
+
+
+knnquery = KNNQuery.apply
+
+
+def queryandgroup(nsample, xyz, new_xyz, feat, idx, offset, new_offset, use_xyz=True, return_indx=False):
+    """pointops.py:648-675: kNN + gather of relative coordinates and features -> (m, nsample, [3+]c)."""
+    _contig(xyz, feat)
+    if new_xyz is None:
+        new_xyz = xyz
+    if idx is None:
+        idx, _ = knnquery(nsample, xyz, new_xyz, offset, new_offset)
+    m, c = new_xyz.shape[0], feat.shape[1]
+    flat = idx.view(-1).long()
+    grouped_xyz = xyz[flat, :].view(m, nsample, 3) - new_xyz.unsqueeze(1)
+    grouped_feat = feat[flat, :].view(m, nsample, c)
+    out = torch.cat((grouped_xyz, grouped_feat), -1) if use_xyz else grouped_feat
+    return (out, idx) if return_indx else out
+
+
+def interpolation(xyz, new_xyz, feat, offset, new_offset, k=3):
+    """pointops.py:756-770: inverse-distance weighted interpolation from the k nearest support points -> (n, c)."""
+    _contig(xyz, new_xyz, feat)
+    idx, dist = knnquery(k, xyz, new_xyz, offset, new_offset)
+    dist_recip = 1.0 / (dist + 1e-8)
+    weight = dist_recip / torch.sum(dist_recip, dim=1, keepdim=True)
+    new_feat = torch.zeros(new_xyz.shape[0], feat.shape[1], dtype=feat.dtype, device=feat.device)
+    for i in range(k):
+        new_feat = new_feat + feat[idx[:, i].long(), :] * weight[:, i].unsqueeze(-1)
+    return new_feat

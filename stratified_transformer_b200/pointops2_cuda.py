@@ -224,3 +224,9 @@ def dot_prod_with_idx_backward_cuda_v2(N, M, h, hdim, n_max, T, grad_out, q, ind
 def furthestsampling_cuda(b, n, xyz, offset, new_offset, tmp, idx):
     _cabi.call("stb200_furthestsampling", int(b), int(n), _f(xyz, "xyz"), _i(offset, "offset"),
                _i(new_offset, "new_offset"), None if tmp is None else _f(tmp, "tmp"), _i(idx, "idx"), _stream())
+
+
+def knnquery_cuda(m, nsample, xyz, new_xyz, offset, new_offset, idx, dist2):
+    """same positional arguments as the reference pybind function (knnquery/knnquery_cuda_kernel.h:7)"""
+    _cabi.call("stb200_knnquery", int(m), int(offset.numel()), int(nsample), _f(xyz, "xyz"), _f(new_xyz, "new_xyz"),
+               _i(offset, "offset"), _i(new_offset, "new_offset"), _i(idx, "idx"), _f(dist2, "dist2"), _stream())

@@ -247,7 +247,6 @@ class PendingLayerIndex:
                            win_offsets if M else None, int(n_win) if M else 0)
             if self.L is not None:
                 pi.c_struct(self.L, backward=True)   # transposed CSR + packed bins, eagerly, on this stream
-                pi.fused_plan()
             built.append(pi)
         self.parts = None
         li = LayerIndex(self.ds_idx, tuple(built))

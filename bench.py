@@ -24,7 +24,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -62,13 +61,6 @@ def parse():
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def hierarchy_counts(n, levels):
-    out = [n]
-    for _ in range(levels - 1):
-        out.append(int(out[-1] * 0.25) + 1)   # TransitionDown, model/stratified_transformer.py:98-101
-    return out
-
-
 def cpu_hot_path(n_points, steps, warmup, threads=None):
     """The reference formulation on the host: numpy/torch index construction + gather/scatter_add attention with
     autograd backward (oracle/), one scene of n_points, full layer schedule.  Returns (points/s, seconds/step)."""

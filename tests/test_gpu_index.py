@@ -214,3 +214,48 @@ def test_fused_window_forward_vs_per_pair_path(golden_dir, name, C, h):
         assert frac > (0.9 if parity == 0 else 0.1)
         if parity == 1:
             assert rows.numel() > 0
+
+
+def test_geometry_prefetcher_matches_serial_builder(golden_dir):
+    """Split-phase construction on a side stream (what bench.py and a training loop use) gives the same pair lists,
+    transposed CSR and packed bins as the serial builder."""
+    from stratified_transformer_b200 import index
+    g = np.load(os.path.join(golden_dir, "index_s3dis_small.npz"))
+    xyz = torch.from_numpy(g["xyz"]).cuda()
+    off = torch.from_numpy(g["offset"]).cuda()
+    w, quant, ds = float(g["window_size"]), float(g["quant_size"]), int(g["downsample_scale"])
+    L = 2 * int((2 * w + 1e-4) // quant)
+    serial = index.build_layer_index(xyz, off, w, quant, ds)
+    pf = index.GeometryPrefetcher([(w, quant, ds, L)])
+    for _ in range(3):      # several rounds: buffers are recycled across submissions
+        pf.submit([xyz], [off], [g["offset"].tolist()])
+        pf.complete()
+        (li,) = pf.take()
+        torch.cuda.synchronize()
+        assert torch.equal(li.downsample_idx, serial.downsample_idx)
+        for p in (0, 1):
+            a, b = li.for_block(p), serial.for_block(p)
+            assert a.M == b.M and a.n_max == b.n_max and a.n_win == b.n_win
+            for name in ("index_0_offsets", "index_1", "rel_idx", "row_order", "win_offsets"):
+                assert torch.equal(getattr(a, name), getattr(b, name)), name
+            ta, tb = a.tcsr, b.tcsr
+            assert torch.equal(ta.t_offsets, tb.t_offsets) and torch.equal(ta.t_pair, tb.t_pair) and torch.equal(ta.t_index0, tb.t_index0)
+
+
+def test_window_attention_under_autocast(golden_dir):
+    """AMP recipe of the reference (use_amp): Linear layers in bf16, pair ops pinned to fp32 by the wrappers."""
+    from stratified_transformer_b200.window_attention import WindowAttention
+    g = np.load(os.path.join(golden_dir, "index_s3dis_small.npz"))
+    xyz, offset = g["xyz"], g["offset"]
+    torch.manual_seed(0)
+    mod = WindowAttention(48, 0.16, 3, 0.01, rel_query=True, rel_key=True, rel_value=True).cuda()
+    pi = build(xyz, offset, 0.16, 0.01, g["downsample_idx"], 0)
+    feats = torch.randn(xyz.shape[0], 48, device="cuda", requires_grad=True)
+    xd = torch.from_numpy(xyz).cuda()
+    ref = mod(feats, xd, pi)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = mod(feats, xd, pi)
+    out.float().sum().backward()
+    assert out.dtype == torch.bfloat16 and feats.grad is not None and torch.isfinite(feats.grad).all()
+    assert (out.float() - ref).abs().max() < 0.05 * ref.abs().max()
+    assert mod.relative_pos_query_table.grad.dtype == torch.float32

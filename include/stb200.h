@@ -246,6 +246,16 @@ int stb200_segment_softmax_forward_rows(int n_rows, const int *rows, int h, cons
 int stb200_knnquery(int m, int b, int nsample, const float *xyz, const float *new_xyz, const int *offset,
                     const int *new_offset, int *idx, float *dist2, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * bf16-storage forward path (inference, BASELINE config 3): q / k / v are bf16 [N,h,16] (device pointers to
+ * __nv_bfloat16), the fp32 tables are rounded to bf16 while being staged, products and sums are fp32, logits and
+ * output are fp32.  Halves the gathered row bytes and the shared-memory bytes per table look-up.  Stated tolerance
+ * against the fp32 path: 2e-2 of the output scale.  Forward only; rel_packed required. */
+int stb200_window_logits_forward_bf16(const stb200_index *ix, int h, int hdim, int L, const void *q_bf16, const void *k_bf16,
+                                      const float *table_q, const float *table_k, float *logits, void *stream);
+int stb200_window_aggregate_forward_bf16(const stb200_index *ix, int h, int hdim, int L, const float *attn, const void *v_bf16,
+                                         const float *table_v, float *output, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

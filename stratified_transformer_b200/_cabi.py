@@ -52,6 +52,8 @@ _SIGNATURES = {
     "stb200_window_logits_backward": [_IX, _c_int, _c_int, _c_int] + [P] * 10,
     "stb200_window_aggregate_forward": [_IX, _c_int, _c_int, _c_int] + [P] * 5,
     "stb200_window_aggregate_backward": [_IX, _c_int, _c_int, _c_int] + [P] * 8,
+    "stb200_window_logits_forward_bf16": [_IX, _c_int, _c_int, _c_int] + [P] * 6,
+    "stb200_window_aggregate_forward_bf16": [_IX, _c_int, _c_int, _c_int] + [P] * 5,
     "stb200_knnquery": [_c_int, _c_int, _c_int, P, P, P, P, P, P, P],
     "stb200_classify_windows": [_c_int, P, P, P, P, P, P, P, P],
     "stb200_window_attention_forward_fused": [_IX, _c_int, P, P, _c_int, _c_int, _c_int] + [P] * 9,

@@ -328,6 +328,27 @@ def window_attention_fused(q, k, v, table_q, table_k, table_v, pair_index):
     return WindowAttentionFused.apply(q, k, v, table_q, table_k, table_v, pair_index)
 
 
+@torch.no_grad()
+def window_attention_inference_bf16(q, k, v, table_q, table_k, table_v, pair_index):
+    """Forward-only pair path with bf16 storage of q / k / v and of the staged tables (BASELINE config 3, inference):
+    logits and softmax in fp32, output fp32 [N, h, d].  Tolerance vs the fp32 path: 2e-2 of the output scale."""
+    N, h, d = q.shape
+    L = table_q.shape[0]
+    q16, k16, v16 = (t.to(torch.bfloat16).contiguous() for t in (q, k, v))
+    tq, tk, tv = (t.float().contiguous() for t in (table_q, table_k, table_v))
+    ix = pair_index.c_struct(L)
+    stream = torch.cuda.current_stream().cuda_stream
+    s = torch.empty(pair_index.M, h, dtype=torch.float32, device=q.device)
+    _cabi.call("stb200_window_logits_forward_bf16", ctypes.byref(ix), h, d, L, q16.data_ptr(), k16.data_ptr(), tq.data_ptr(),
+               tk.data_ptr(), s.data_ptr(), stream)
+    p = torch.empty_like(s)
+    pointops_cuda.segment_softmax_forward_cuda(N, pair_index.M, h, s, None, pair_index.index_0_offsets, p)
+    out = torch.empty(N, h, d, dtype=torch.float32, device=q.device)
+    _cabi.call("stb200_window_aggregate_forward_bf16", ctypes.byref(ix), h, d, L, p.data_ptr(), v16.data_ptr(), tv.data_ptr(),
+               out.data_ptr(), stream)
+    return out
+
+
 def segment_softmax(a, index0_offsets, b=None):
     return SegmentSoftmax.apply(a, b, index0_offsets)
 

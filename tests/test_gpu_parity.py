@@ -269,3 +269,19 @@ def test_folded_row_gradient_path(monkeypatch):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("N,M,h,L", [(3500, 80000, 6, 80), (700, 30000, 3, 64), (300, 6000, 24, 64)])
+def test_bf16_inference_forward(N, M, h, L):
+    """bf16-storage forward (BASELINE config 3): stated tolerance 2e-2 of the output scale against the fp64 oracle."""
+    from stratified_transformer_b200 import pointops
+    from stratified_transformer_b200.index import PairIndex
+    cpu, dev = make_case(N, M, h, 16, L, seed=8, dist="randn")
+    for key in ("tq", "tk", "tv"):
+        cpu[key] = cpu[key] * 0.1
+        dev[key] = dev[key] * 0.1
+    want = oracle_layer(cpu)["out"]
+    pi = PairIndex(dev["offsets"], dev["i1"], dev["rel"].contiguous(), 0, int(dev["i1"].numel()))
+    got = pointops.window_attention_inference_bf16(dev["q"], dev["k"], dev["v"], dev["tq"], dev["tk"], dev["tv"], pi)
+    err = (got.double().cpu() - want).abs().max().item()
+    assert err <= 2e-2 * want.abs().max().item(), err

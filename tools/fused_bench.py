@@ -39,3 +39,17 @@ for parity in (0, 1):
     frac_rows = 1.0 - rows.numel() / N
     print(f"parity {parity}: N={N} M={M} windows={pi.n_win} fused windows={int(flags.sum())} ({frac_rows:.1%} of rows)  "
           f"per-pair fwd {timed(per_pair):.3f} ms   fused kernel (eligible windows only) {timed(fused):.3f} ms", flush=True)
+
+# bf16-storage forward (inference) vs fp32 per-pair forward, parity 0
+pi = li.for_block(0); M = pi.M; ix = pi.c_struct(L)
+q16, k16, v16 = (t.to(torch.bfloat16).contiguous() for t in (q, k, v))
+s = torch.empty(M, h, device="cuda"); p = torch.empty(M, h, device="cuda"); out = torch.empty(N, h, d, device="cuda")
+def fwd32():
+    _cabi.call("stb200_window_logits_forward", ctypes.byref(ix), h, d, L, q.data_ptr(), k.data_ptr(), tq.data_ptr(), tk.data_ptr(), s.data_ptr(), stream)
+    ext.segment_softmax_forward_cuda(N, M, h, s, None, pi.index_0_offsets, p)
+    _cabi.call("stb200_window_aggregate_forward", ctypes.byref(ix), h, d, L, p.data_ptr(), v.data_ptr(), tv.data_ptr(), out.data_ptr(), stream)
+def fwd16():
+    _cabi.call("stb200_window_logits_forward_bf16", ctypes.byref(ix), h, d, L, q16.data_ptr(), k16.data_ptr(), tq.data_ptr(), tk.data_ptr(), s.data_ptr(), stream)
+    ext.segment_softmax_forward_cuda(N, M, h, s, None, pi.index_0_offsets, p)
+    _cabi.call("stb200_window_aggregate_forward_bf16", ctypes.byref(ix), h, d, L, p.data_ptr(), v16.data_ptr(), tv.data_ptr(), out.data_ptr(), stream)
+print(f"forward, layer-0 shape: fp32 {timed(fwd32):.3f} ms   bf16 storage {timed(fwd16):.3f} ms", flush=True)

@@ -113,7 +113,7 @@ def run_reference_arm(a):
     if rank != 0:
         return
     total = a.steps + a.warmup
-    n = a.cpu_sample_points or int(max(1500, min(8000, 60000 / max(total, 1))))
+    n = a.cpu_sample_points or int(max(4000, min(30000, 400000 / max(total, 1))))
     cores = os.cpu_count()
     pps, dt = cpu_hot_path(n, a.steps, a.warmup)
     sample = f"1 synthetic S3DIS-shape scene cropped to {n} points, full 4-layer / 12-block schedule, fp32, torch CPU {cores} threads"
@@ -475,7 +475,7 @@ def main():
 
     cpu_baseline = None
     if not a.no_cpu_baseline and world == 1:
-        n = a.cpu_sample_points or 6000
+        n = a.cpu_sample_points or 24000
         pps, dt = cpu_hot_path(n, 1, 1)
         cpu_baseline = {"value": pps, "unit": "points/s", "cores": os.cpu_count(), "kind": "port",
                         "sample": f"1 scene cropped to {n} points, full 4-layer/12-block schedule, 1 warm-up + 1 timed pass ({dt:.1f} s)"}

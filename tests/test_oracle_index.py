@@ -107,3 +107,42 @@ def test_fps_block_size():
     assert fps_oracle.block_size(1000) == 512
     assert fps_oracle.block_size(1024) == 1024
     assert fps_oracle.block_size(5) == 4
+
+
+@pytest.mark.parametrize("seed,lattice", [(0, False), (1, True), (2, False)])
+def test_index_oracle_equals_definition_brute_force(seed, lattice):
+    """Independent of the reference's tensor code: per query, keys = points of its small window (dense), then FPS-sampled
+    points of its large window whose floor-div window coordinate differs (sparse) — straight from SURVEY B.4."""
+    rng = np.random.default_rng(seed)
+    sizes = [230, 170]
+    xyz = rng.uniform(0, 1.3, (sum(sizes), 3))
+    if lattice:
+        xyz = np.round(xyz / 0.04) * 0.04
+    xyz = xyz.astype(np.float32)
+    offset = np.cumsum(sizes).astype(np.int32)
+    w, ds = 0.16, 4
+    batch = io.batch_from_offset(offset)
+    ds_idx = fps_oracle.furthestsampling(xyz, offset, io.fps_new_offset(offset, ds))
+    sampled = np.zeros(xyz.shape[0], bool)
+    sampled[ds_idx] = True
+    w3 = np.full(3, w, np.float32)
+    for parity in (0, 1):
+        got = io.build_layer_index(xyz, offset, w, ds, ds_idx, parity)
+        if parity == 0:
+            small = io.voxel_grid(xyz, batch, w3, None)
+            large = io.voxel_grid(xyz, batch, (np.float32(2) * w3).astype(np.float32), None)
+            wc = io.floor_div_f32((xyz - xyz.min(0)).astype(np.float32), w3)
+        else:
+            mn = xyz.min(0)
+            half, full = (np.float32(0.5) * w3).astype(np.float32), w3
+            small = io.voxel_grid((xyz + half).astype(np.float32), batch, w3, mn)
+            large = io.voxel_grid((xyz + full).astype(np.float32), batch, (np.float32(2) * w3).astype(np.float32), mn)
+            wc = io.floor_div_f32(((xyz + half).astype(np.float32) - mn).astype(np.float32), w3)
+        keys = []
+        for a in range(xyz.shape[0]):
+            dense = np.nonzero(small == small[a])[0]
+            sparse = np.nonzero((large == large[a]) & sampled & (wc != wc[a]).any(1))[0]
+            keys.append(np.concatenate([dense, sparse]))
+        want_off = np.concatenate([[0], np.cumsum([len(k) for k in keys])])
+        assert np.array_equal(got["offsets"], want_off)
+        assert np.array_equal(got["index_1"], np.concatenate(keys))

@@ -50,8 +50,18 @@ struct SegParams {
     float *out2;           // table_grad FOLD: [N, h, D] gradient rows, added to with red.global.add
 };
 
-// Copy one head group of a [L,h,D,3] table into shared memory as [axis][l][hh][c].
-template <int D, int HG>
+// Copy one head group of a [L,h,D,3] table into shared memory as [axis][l][hh][copy][c].
+// A 16-float row is 64 B = half of the 32 banks, and the lanes of one LDS.128 quarter-warp (two lane groups) read
+// two different, data-dependent rows: with a single copy they collide whenever both rows fall into the same half
+// (always, for an even head group in seg_reduce; half of the time otherwise).  For D = 16 the table is therefore
+// stored twice, copy c in bank half c, and lane group s reads copy s & 1: every look-up is conflict-free.
+// A 32-float row already spans all banks and needs one copy.  seg_dot keeps one copy as well: its lane groups walk
+// (pair, head) items, so neighbouring groups mostly hit different halves already (1-14 % conflicts measured), and with
+// two staged tables the second copy costs more in lost L1 capacity for the row gathers than the conflicts do.
+template <int D>
+constexpr int kReduceTableCopies = D == 16 ? 2 : 1;
+
+template <int D, int HG, int NC>
 __device__ __forceinline__ void stage_table(float *dst, const float *__restrict__ src, int L, int h, int h0) {
     const int total = 3 * L * HG * D;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
@@ -59,7 +69,9 @@ __device__ __forceinline__ void stage_table(float *dst, const float *__restrict_
         const int hh = (i / D) % HG;
         const int l = (i / (D * HG)) % L;
         const int a = i / (D * HG * L);
-        dst[i] = __ldg(src + ((size_t)(l * h + h0 + hh) * D + c) * 3 + a);
+        const float v = __ldg(src + ((size_t)(l * h + h0 + hh) * D + c) * 3 + a);
+#pragma unroll
+        for (int cp = 0; cp < NC; ++cp) dst[((i / D) * NC + cp) * D + c] = v;
     }
 }
 
@@ -74,13 +86,14 @@ __device__ __forceinline__ unsigned pack_bins(const int *__restrict__ r, int L) 
 }
 
 // E[c..c+3] = (T[0][r0] + T[1][r1]) + T[2][r2] for one head chunk (left-to-right adds like the reference)
-template <int D, int HG>
-__device__ __forceinline__ float4 table_sum4(const float *ts, int L, int r0, int r1, int r2, int hh, int g) {
+// `gc` = copy * G + g: the lane's float4 column inside the (duplicated) row, see stage_table
+template <int D, int HG, int NC>
+__device__ __forceinline__ float4 table_sum4(const float *ts, int L, int r0, int r1, int r2, int hh, int gc) {
     const float4 *t4 = reinterpret_cast<const float4 *>(ts);
-    constexpr int G = D / 4;
-    const float4 a = t4[((0 * L + r0) * HG + hh) * G + g];
-    const float4 b = t4[((1 * L + r1) * HG + hh) * G + g];
-    const float4 c = t4[((2 * L + r2) * HG + hh) * G + g];
+    constexpr int G = D / 4 * NC;
+    const float4 a = t4[((0 * L + r0) * HG + hh) * G + gc];
+    const float4 b = t4[((1 * L + r1) * HG + hh) * G + gc];
+    const float4 c = t4[((2 * L + r2) * HG + hh) * G + gc];
     return f4_add(f4_add(a, b), c);
 }
 
@@ -90,8 +103,10 @@ __device__ __forceinline__ float4 table_sum4(const float *ts, int L, int r0, int
 //   dot_prod_with_idx v3 EX|EY        x=q[n]        y=k[i1]      Tx=table_q Ty=table_k
 //   step2-rpv bwd gattn  XY|EX        x=grad_out[n] y=v[i1]      Tx=table_v
 // A warp owns a query; its len*HG (pair, head) items are spread over 32/G lane groups of G=D/4 lanes.
+// Table variants run 512 threads per CTA; capping them at 64 registers keeps two CTAs (32 warps) resident per SM,
+// which hides the shared-memory look-up latency better than the 80-register / 16-warp build (measured: -20 %).
 template <int D, int HG, bool XY, bool EX, bool EY>
-__global__ void __launch_bounds__(kMaxSegThreads) seg_dot_kernel(const SegParams p) {
+__global__ void __launch_bounds__(kMaxSegThreads, (EX || EY) ? 2 : 1) seg_dot_kernel(const SegParams p) {
     extern __shared__ float4 smem4[];
     float *smem = reinterpret_cast<float *>(smem4);
     constexpr int G = D / 4, NS = kWarp / G;
@@ -101,8 +116,8 @@ __global__ void __launch_bounds__(kMaxSegThreads) seg_dot_kernel(const SegParams
     float *tx = smem;
     float *ty = tx + (EX ? tsz : 0);
     float *xs = ty + (EY ? tsz : 0);
-    if (EX) stage_table<D, HG>(tx, p.Tx, L, h, h0);
-    if (EY) stage_table<D, HG>(ty, p.Ty, L, h, h0);
+    if (EX) stage_table<D, HG, 1>(tx, p.Tx, L, h, h0);
+    if (EY) stage_table<D, HG, 1>(ty, p.Ty, L, h, h0);
     if (EX || EY) __syncthreads();
 
     const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp, nwarps = blockDim.x / kWarp;
@@ -150,8 +165,8 @@ __global__ void __launch_bounds__(kMaxSegThreads) seg_dot_kernel(const SegParams
                         if (EX || EY) {
                             const unsigned pk = __shfl_sync(0xffffffffu, pk_l, pl[u]);
                             const int r0 = pk & 0x3ff, r1 = (pk >> 10) & 0x3ff, r2 = pk >> 20;
-                            if (EX) acc = f4_dot(x4, table_sum4<D, HG>(tx, L, r0, r1, r2, hh[u], g), acc);
-                            if (EY) acc = f4_dot(y4[u], table_sum4<D, HG>(ty, L, r0, r1, r2, hh[u], g), acc);
+                            if (EX) acc = f4_dot(x4, table_sum4<D, HG, 1>(tx, L, r0, r1, r2, hh[u], g), acc);
+                            if (EY) acc = f4_dot(y4[u], table_sum4<D, HG, 1>(ty, L, r0, r1, r2, hh[u], g), acc);
                         }
                         acc = group_sum<G>(acc);
                         if (act[u] && g == 0) p.out[(size_t)(start + c0 + pl[u]) * h + h0 + hh[u]] = acc;
@@ -179,11 +194,12 @@ __global__ void __launch_bounds__(kMaxSegThreads) seg_reduce_kernel(const SegPar
     const int L = p.L, h = p.h, C = p.h * D;
     const int h0 = blockIdx.y * HG;
     if (HAS_T) {
-        stage_table<D, HG>(ts, p.Tx, L, h, h0);
+        stage_table<D, HG, kReduceTableCopies<D>>(ts, p.Tx, L, h, h0);
         __syncthreads();
     }
     const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp, nwarps = blockDim.x / kWarp;
     const int slot = lane / G, g = lane % G;
+    const int gc = (kReduceTableCopies<D> == 2 ? (slot & 1) * G : 0) + g;
 
     for (int base_n = blockIdx.x * kRowsPerChunk; base_n < p.N; base_n += gridDim.x * kRowsPerChunk) {
         const int end_n = min(p.N, base_n + kRowsPerChunk);
@@ -219,7 +235,7 @@ __global__ void __launch_bounds__(kMaxSegThreads) seg_reduce_kernel(const SegPar
                             wv[u][hh] = act[u] ? ld_stream(p.w + (size_t)m * h + h0 + hh) : 0.f;
                             val[u][hh] = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (HAS_Y) val[u][hh] = ld_row4(p.Y + (size_t)j * C + (h0 + hh) * D + 4 * g);
-                            if (HAS_T) val[u][hh] = f4_add(table_sum4<D, HG>(ts, L, r0, r1, r2, hh, g), val[u][hh]);
+                            if (HAS_T) val[u][hh] = f4_add(table_sum4<D, HG, kReduceTableCopies<D>>(ts, L, r0, r1, r2, hh, gc), val[u][hh]);
                         }
                     }
 #pragma unroll
@@ -634,17 +650,31 @@ __global__ void __launch_bounds__(kThreads) segment_softmax_bwd_hp_kernel(int N,
 
 // ------------------------------------------------------------------------------------------------
 // host-side launch helpers
-// threads per CTA of the segment kernels: tuning knob STB200_SEG_THREADS (256 / 512), default by table use
-static int seg_threads(int ntables) {
+// threads per CTA of the segment kernels: tuning knobs STB200_SEG_THREADS (both) / STB200_SEGRED_THREADS (seg_reduce
+// only), multiples of 32 up to 512; default by table use
+static int seg_threads(int ntables, bool reduce = false) {
     static const int env = getenv("STB200_SEG_THREADS") ? atoi(getenv("STB200_SEG_THREADS")) : 0;
-    if (env == 256 || env == 512) return env;
-    return ntables > 0 ? 512 : kThreads;   // table variants are shared-memory / latency bound: more warps per staged table copy
+    static const int env_red = getenv("STB200_SEGRED_THREADS") ? atoi(getenv("STB200_SEGRED_THREADS")) : 0;
+    const int e = reduce && env_red ? env_red : env;
+    if (e >= 64 && e <= kMaxSegThreads && e % kWarp == 0) return e;
+    // seg_dot with tables: shared-memory / latency bound, 2 x 512 threads per SM share the staged tables best;
+    // seg_reduce (about 100 registers per thread) does slightly better with two 256-thread CTAs, which also still fit
+    // beside a resident FPS CTA of the geometry stream
+    return ntables > 0 && !reduce ? 512 : kThreads;
+}
+
+// CTAs per launch = resident capacity x "waves".  More than one wave lets the hardware block scheduler rebalance when
+// another stream (the geometry prefetch) holds part of the machine: with exactly one wave, every CTA that does not fit
+// at launch runs after the others finish and doubles the kernel time.  Tuning knob: STB200_SEG_WAVES.
+static int seg_waves() {
+    static const int env = getenv("STB200_SEG_WAVES") ? atoi(getenv("STB200_SEG_WAVES")) : 1;
+    return max(1, env);
 }
 
 static int grid_rows(int N, size_t smem, int groups) {
     const int chunks = (N + kRowsPerChunk - 1) / kRowsPerChunk;
     const int ctas_per_sm = (int)max((size_t)1, min((size_t)4, (size_t)(220 * 1024) / max(smem, (size_t)1)));
-    return max(1, min(chunks, (kNumSMs * ctas_per_sm + groups - 1) / groups));
+    return max(1, min(chunks, (kNumSMs * ctas_per_sm * seg_waves() + groups - 1) / groups));
 }
 
 template <typename K>
@@ -666,7 +696,8 @@ static int prep_smem(K kernel, size_t bytes) {
 // heads per CTA: as many as divide h, up to 4, while the staged tables stay under ~100 KB
 static int pick_hg(int h, int D, int L, int ntables) {
     int cap = 4;
-    while (cap > 1 && (size_t)ntables * 3 * L * cap * D * 4 > 100 * 1024) --cap;
+    const int copies = ntables == 1 && D == 16 ? 2 : 1;   // upper bound: kReduceTableCopies
+    while (cap > 1 && (size_t)ntables * 3 * L * cap * D * copies * 4 > 100 * 1024) --cap;
     return largest_head_group(h, cap);
 }
 
@@ -718,13 +749,13 @@ static int launch_seg_dot(int D, const SegParams &p, int M, const char *name, cu
 
 template <int D, int HG, bool HAS_Y, bool HAS_T, bool PERM>
 static int launch_seg_reduce_hg(const SegParams &p, int M, const char *name, cudaStream_t s) {
-    const size_t smem = (size_t)HAS_T * 3 * p.L * HG * D * sizeof(float);
+    const size_t smem = (size_t)HAS_T * 3 * p.L * HG * D * kReduceTableCopies<D> * sizeof(float);
     auto kern = seg_reduce_kernel<D, HG, HAS_Y, HAS_T, PERM>;
     if (int rc = prep_smem(kern, smem)) return rc;
     dim3 grid(grid_rows(p.N, smem, p.h / HG), p.h / HG);
     {
         KernelScope ks(name, seg_bytes(p, D, M, false, HAS_Y, true, HAS_Y, PERM, HAS_T, false), s);
-        kern<<<grid, seg_threads(HAS_T && !PERM), smem, s>>>(p);
+        kern<<<grid, seg_threads(HAS_T && !PERM, true), smem, s>>>(p);
     }
     return check_launch(name);
 }
@@ -760,7 +791,8 @@ static int launch_table_grad_hg(const SegParams &p, int M, const char *name, cud
     const int tiles = (p.N + kTQ - 1) / kTQ;
     const int groups = p.h / HGC;
     const int ctas_per_sm = max(1, min(4, (int)((226 * 1024) / (smem + 1024))));
-    const int gx = max(1, min(tiles, (kNumSMs * ctas_per_sm + groups - 1) / groups));
+    static const int tg_waves = max(1, getenv("STB200_TG_WAVES") ? atoi(getenv("STB200_TG_WAVES")) : 1);
+    const int gx = max(1, min(tiles, (kNumSMs * ctas_per_sm * tg_waves + groups - 1) / groups));
     for (int pass = 0; pass < R; pass += 256) {
         KernelScope ks(name, seg_bytes(p, D, M, true, false, true, false, PERM, 1, false) - 4.0 * p.N * p.h * D + (fold ? 8.0 * p.N * p.h * D : 0.0), s);
         kern<<<dim3(gx, groups), kTGThreads(HGC), smem, s>>>(p, pass, Rpad);

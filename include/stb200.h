@@ -205,7 +205,16 @@ typedef struct stb200_index {
     const unsigned *t_rel_packed; /* [M] optional, bins of pair t_pair[t] */
     const int *row_order;         /* [N] optional: process rows in this order (e.g. points sorted by window, from the
                                      pair builder) so that neighbouring warps gather the same k/v rows */
+    const int *len_order;         /* [N] optional: queries sorted by pair count (stb200_length_order on index0_offsets) */
+    const int *t_len_order;       /* [N] optional: keys sorted by incoming pair count (stb200_length_order on t_offsets);
+                                     both are balance hints for the table-gradient kernels, whose 32-row tiles give one
+                                     lane per row: rows of equal length keep all lanes busy */
 } stb200_index;
+
+/* order[] = the rows listed in base_order (NULL: 0..N-1) stably sorted by pair count offsets[r+1]-offsets[r]. */
+size_t stb200_length_order_workspace_bytes(int N);
+int stb200_length_order(int N, const int *offsets, const int *base_order, int *order, void *workspace,
+                        size_t workspace_bytes, void *stream);
 
 /* out[i] = r0 | r1 << 10 | r2 << 20 of pair (perm ? perm[i] : i), bins clamped to [0, L) */
 int stb200_pack_rel(int M, int L, const int *rel_idx, const int *perm, unsigned *out, void *stream);

@@ -19,7 +19,7 @@ class IndexStruct(ctypes.Structure):
     _fields_ = [("N", ctypes.c_int), ("M", ctypes.c_int), ("index0_offsets", ctypes.c_void_p), ("index1", ctypes.c_void_p),
                 ("rel_idx", ctypes.c_void_p), ("t_offsets", ctypes.c_void_p), ("t_pair", ctypes.c_void_p),
                 ("t_index0", ctypes.c_void_p), ("rel_packed", ctypes.c_void_p), ("t_rel_packed", ctypes.c_void_p),
-                ("row_order", ctypes.c_void_p)]
+                ("row_order", ctypes.c_void_p), ("len_order", ctypes.c_void_p), ("t_len_order", ctypes.c_void_p)]
 
 
 _IX = ctypes.POINTER(IndexStruct)
@@ -27,6 +27,7 @@ _IX = ctypes.POINTER(IndexStruct)
 # name -> argtypes (every function returns int unless listed in _RESTYPES)
 _SIGNATURES = {
     "stb200_transpose_csr": [_c_int, _c_int, P, P, P, P, P, P, _c_size_t, P],
+    "stb200_length_order": [_c_int, P, P, P, P, _c_size_t, P],
     "stb200_attention_step1_forward_v2": [_c_int] * 4 + [_c_uint] + [P] * 6,
     "stb200_attention_step1_backward_v2": [_c_int] * 4 + [_c_uint] + [P] * 11,
     "stb200_dot_prod_with_idx_forward_v3": [_c_int] * 6 + [P] * 9,
@@ -65,6 +66,7 @@ _RESTYPES = {
     "stb200_launch_count": (ctypes.c_longlong, []),
     "stb200_version": (_c_int, []),
     "stb200_transpose_csr_workspace_bytes": (_c_size_t, [_c_int, _c_int]),
+    "stb200_length_order_workspace_bytes": (_c_size_t, [_c_int]),
     "stb200_pair_builder_workspace_bytes": (_c_size_t, [_c_int]),
     "stb200_fused_max_keys": (_c_int, []),
     "stb200_profile_enable": (None, [_c_int]),

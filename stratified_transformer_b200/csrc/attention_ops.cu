@@ -46,8 +46,6 @@ struct SegParams {
     const unsigned *packed; // optional: the three bins of each segment slot packed 10 bits each (replaces rel_idx)
     float *out;
     int accumulate;
-    const float *T2;       // table_grad FOLD: table whose rows multiply the histograms -> row gradients
-    float *out2;           // table_grad FOLD: [N, h, D] gradient rows, added to with red.global.add
 };
 
 // Copy one head group of a [L,h,D,3] table into shared memory as [axis][l][hh][copy][c].
@@ -298,12 +296,12 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], 
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-template <int D, int HGC, bool PERM, bool MULTI, bool FOLD>
+template <int D, int HGC, bool PERM, bool MULTI>
 __global__ void __launch_bounds__(kTGThreads(HGC), (D == 16 ? 2 : 1)) table_grad_kernel(const SegParams p, int row_pass_base, int Rpad) {
     extern __shared__ float4 smem4[];
     constexpr int NT = D / 8;                               // n-tiles (8 channels each)
     constexpr int NW = kTGThreads(HGC) / kWarp;             // warps
-    constexpr int TPW = (16 * NT + NW - 1) / NW;            // (m-tile, n-tile) pairs per warp (<= 256 table rows per pass)
+    constexpr int UPW = (HGC * 16 + NW - 1) / NW;           // (head, m-tile) units per warp (<= 256 table rows per pass)
     constexpr int XP = D + 8;                               // pitch of the X tile: conflict-free B-fragment loads
     const int L = p.L, h = p.h, R = 3 * L;
     const int Rp = min(256, R - row_pass_base);             // table rows handled in this pass
@@ -313,40 +311,69 @@ __global__ void __launch_bounds__(kTGThreads(HGC), (D == 16 ? 2 : 1)) table_grad
     float *Xs = W + HGC * Rpad * kTQP;                      // [HGC][kTQ][XP]
     float *sw = Xs + HGC * kTQ * XP;                        // [HGC][kPC] weights
     unsigned *pk = reinterpret_cast<unsigned *>(sw + HGC * kPC);   // [kPC] r0 | r1<<8 | r2<<16
-    int *soff = reinterpret_cast<int *>(pk + kPC);          // [kTQ + 1] offsets of the tile's rows
-    float *Tt = reinterpret_cast<float *>(soff + kTQ + 8);  // FOLD: [D][Rpad + 4] transposed table of the current head
-    const int RTP = Rpad + 4;
+    int *soff = reinterpret_cast<int *>(pk + kPC);          // [kTQ + 1] staged-list offsets of the tile's rows
+    int *gst = soff + kTQ + 8;                              // [kTQ] where each row's pairs start in the CSR
+    int *rown = gst + kTQ;                                  // [kTQ] row ids (-1 beyond N)
+    static_assert(kTQ == kWarp, "the tile prologue scans the row lengths in one warp");
     const int tid = threadIdx.x, lane = tid % kWarp, warp = tid / kWarp, nthr = blockDim.x;
     const int gid = lane >> 2, tig = lane & 3;
 
-    float acc[HGC][TPW][4];
+    float acc[UPW][NT][4];
 #pragma unroll
-    for (int a = 0; a < HGC; ++a)
+    for (int a = 0; a < UPW; ++a)
 #pragma unroll
-        for (int b = 0; b < TPW; ++b)
+        for (int b = 0; b < NT; ++b)
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
 
     for (int base_n = blockIdx.x * kTQ; base_n < p.N; base_n += gridDim.x * kTQ) {
         __syncthreads();   // previous tile fully consumed
-        if (tid <= kTQ) soff[tid] = __ldg(p.offsets + min(base_n + tid, p.N));
-        for (int i = tid; i < HGC * Rpad * kTQP; i += nthr) W[i] = 0.f;
+        // The tile's rows are row_order[base_n .. base_n+31] (or consecutive rows).  Their pair segments need not be
+        // adjacent in the CSR: soff[] is the prefix sum of the row lengths (positions inside the staged pair list),
+        // gst[] the global start of each row's segment.  With rows sorted by length (len_order) all lanes of the
+        // histogram phase below run the same number of iterations.
+        if (warp == 0) {
+            const int r = base_n + lane;
+            int n = -1, gs = 0, len = 0;
+            if (r < p.N) {
+                n = p.row_order ? __ldg(p.row_order + r) : r;
+                gs = __ldg(p.offsets + n);
+                len = __ldg(p.offsets + n + 1) - gs;
+            }
+            int incl = len;
+#pragma unroll
+            for (int o = 1; o < kWarp; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            soff[lane] = incl - len;
+            if (lane == kWarp - 1) soff[kTQ] = incl;
+            gst[lane] = gs;
+            rown[lane] = n;
+        }
+        for (int i = tid; i < HGC * Rpad * kTQP / 4; i += nthr) smem4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
         for (int i = tid; i < HGC * kTQ * (D / 4); i += nthr) {
             const int hh = i / (kTQ * (D / 4)), t = (i / (D / 4)) % kTQ, c4 = i % (D / 4);
-            const int n = base_n + t;
-            const float4 v = n < p.N ? ld_row4(p.X + ((size_t)n * h + h0 + hh) * D + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int n = rown[t];
+            const float4 v = n >= 0 ? ld_row4(p.X + ((size_t)n * h + h0 + hh) * D + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
             *reinterpret_cast<float4 *>(Xs + (hh * kTQ + t) * XP + 4 * c4) = v;
         }
-        __syncthreads();
-        const int m0 = soff[0], m1 = soff[kTQ];
+        const int m1 = soff[kTQ];
         // ---- histograms of all heads of the group, kPC pairs at a time
-        for (int c0 = m0; c0 < m1; c0 += kPC) {
+        for (int c0 = 0; c0 < m1; c0 += kPC) {
             const int cn = min(kPC, m1 - c0);
-            if (c0 > m0) __syncthreads();   // previous chunk consumed
+            if (c0 > 0) __syncthreads();   // previous chunk consumed
             for (int i = tid; i < cn; i += nthr) {
-                const int m = PERM ? __ldg(p.pair_id + c0 + i) : c0 + i;
+                const int li = c0 + i;
+                int t = 0;   // row of staged position li: the last row starting at or before it
+#pragma unroll
+                for (int step = kTQ / 2; step; step >>= 1)
+                    if (soff[t + step] <= li) t += step;
+                const int gpos = gst[t] + (li - soff[t]);
+                const int m = PERM ? __ldg(p.pair_id + gpos) : gpos;
                 if (p.packed) {
-                    const unsigned q = __ldg(p.packed + c0 + i);   // 10-bit fields -> 8-bit fields
+                    const unsigned q = __ldg(p.packed + gpos);   // 10-bit fields -> 8-bit fields
                     pk[i] = (q & 0xffu) | (((q >> 10) & 0xffu) << 8) | (((q >> 20) & 0xffu) << 16);
                 } else {
                     const unsigned r0 = clampi(__ldg(p.rel_idx + 3 * (size_t)m + 0), L - 1);
@@ -375,91 +402,51 @@ __global__ void __launch_bounds__(kTGThreads(HGC), (D == 16 ? 2 : 1)) table_grad
             }
         }
         __syncthreads();
-        // ---- C += W^T X  (rows of W^T = table rows, k = tile rows, n = channels)
+        // ---- C += W^T X  (rows of W^T = table rows, k = tile rows, n = channels).  A warp owns (head, m-tile) units:
+        // the W fragment of a k-step is loaded and split once and used for every channel tile.
 #pragma unroll
-        for (int hh = 0; hh < HGC; ++hh) {
-            if (FOLD) {   // transposed table of this head: Tt[c][(axis, l)], zero beyond the last table row
-                if (hh > 0) __syncthreads();
-                for (int i = tid; i < L * D * 3; i += nthr) {
-                    const int l = i / (D * 3), e = i - l * (D * 3);
-                    const int c = e / 3, a = e - c * 3;
-                    Tt[c * RTP + a * L + l] = __ldg(p.T2 + (size_t)(l * h + h0 + hh) * (D * 3) + e);
-                }
-                for (int i = tid; i < D * (Rpad - R); i += nthr) Tt[(i / (Rpad - R)) * RTP + R + i % (Rpad - R)] = 0.f;
-                __syncthreads();
-            }
+        for (int j = 0; j < UPW; ++j) {
+            const int u = warp + j * NW;
+            if (u < HGC * n_mt) {   // warp-uniform
+                const int hh = u / n_mt, mt = u - hh * n_mt;
+                const float *wa = W + (hh * Rpad + mt * 16 + gid) * kTQP + tig;
+                const float *xb = Xs + (hh * kTQ + tig) * XP + gid;
 #pragma unroll
-            for (int tp = 0; tp < TPW; ++tp) {
-                const int tile = warp + tp * NW;
-                const int mt = tile / NT, nt = tile % NT;
-                if (mt < n_mt) {
-                    const float *wa = W + (hh * Rpad + mt * 16 + gid) * kTQP + tig;
-                    const float *xb = Xs + (hh * kTQ + tig) * XP + nt * 8 + gid;
+                for (int k0 = 0; k0 < kTQ; k0 += 8) {
+                    unsigned ah[4], al[4];
+                    split_tf32(wa[k0], ah[0], al[0]);
+                    split_tf32(wa[8 * kTQP + k0], ah[1], al[1]);
+                    split_tf32(wa[k0 + 4], ah[2], al[2]);
+                    split_tf32(wa[8 * kTQP + k0 + 4], ah[3], al[3]);
 #pragma unroll
-                    for (int k0 = 0; k0 < kTQ; k0 += 8) {
-                        unsigned ah[4], al[4], bh[2], bl[2];
-                        split_tf32(wa[k0], ah[0], al[0]);
-                        split_tf32(wa[8 * kTQP + k0], ah[1], al[1]);
-                        split_tf32(wa[k0 + 4], ah[2], al[2]);
-                        split_tf32(wa[8 * kTQP + k0 + 4], ah[3], al[3]);
-                        split_tf32(xb[k0 * XP], bh[0], bl[0]);
-                        split_tf32(xb[(k0 + 4) * XP], bh[1], bl[1]);
-                        mma_tf32(acc[hh][tp], al, bh);
-                        mma_tf32(acc[hh][tp], ah, bl);
-                        mma_tf32(acc[hh][tp], ah, bh);
-                    }
-                }
-            }
-            if (FOLD) {
-                // ---- G[t][c] = sum_rows W[row][t] * T[row][c]: the rel-pos part of the row gradient (grad_q / grad_k),
-                // (kTQ/16) x NT output tiles, the table-row range split in two halves -> 2 * (kTQ/16) * NT units per head,
-                // handed out from the last warp downwards (those warps own fewer table-gradient tiles)
-                constexpr int UNITS = 2 * (kTQ / 16) * NT;
-                const int ksteps = Rpad / 8;
-                for (int u = NW - 1 - warp; u < UNITS; u += NW) {
-                    const int half = u & 1, mt2 = (u >> 1) % (kTQ / 16), nt = (u >> 1) / (kTQ / 16);
-                    const int kb = half ? ksteps / 2 : 0, ke = half ? ksteps : ksteps / 2;
-                    float g[4] = {0.f, 0.f, 0.f, 0.f};
-                    const float *wa = W + (hh * Rpad + tig) * kTQP + mt2 * 16 + gid;
-                    const float *tb = Tt + (nt * 8 + gid) * RTP + tig;
-                    for (int ks = kb; ks < ke; ++ks) {
-                        const int k0 = ks * 8;
-                        unsigned ah[4], al[4], bh[2], bl[2];
-                        split_tf32(wa[k0 * kTQP], ah[0], al[0]);
-                        split_tf32(wa[k0 * kTQP + 8], ah[1], al[1]);
-                        split_tf32(wa[(k0 + 4) * kTQP], ah[2], al[2]);
-                        split_tf32(wa[(k0 + 4) * kTQP + 8], ah[3], al[3]);
-                        split_tf32(tb[k0], bh[0], bl[0]);
-                        split_tf32(tb[k0 + 4], bh[1], bl[1]);
-                        mma_tf32(g, al, bh);
-                        mma_tf32(g, ah, bl);
-                        mma_tf32(g, ah, bh);
-                    }
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int n = base_n + mt2 * 16 + gid + (c >= 2 ? 8 : 0);
-                        if (n < p.N) atomicAdd(p.out2 + ((size_t)n * h + h0 + hh) * D + nt * 8 + 2 * tig + (c & 1), g[c]);
+                    for (int nt = 0; nt < NT; ++nt) {
+                        unsigned bh[2], bl[2];
+                        split_tf32(xb[k0 * XP + nt * 8], bh[0], bl[0]);
+                        split_tf32(xb[(k0 + 4) * XP + nt * 8], bh[1], bl[1]);
+                        mma_tf32(acc[j][nt], al, bh);
+                        mma_tf32(acc[j][nt], ah, bl);
+                        mma_tf32(acc[j][nt], ah, bh);
                     }
                 }
             }
         }
     }
 #pragma unroll
-    for (int hh = 0; hh < HGC; ++hh)
+    for (int j = 0; j < UPW; ++j) {
+        const int u = warp + j * NW;
+        if (u >= HGC * n_mt) continue;
+        const int hh = u / n_mt, mt = u - hh * n_mt;
 #pragma unroll
-        for (int tp = 0; tp < TPW; ++tp) {
-            const int tile = warp + tp * NW;
-            const int mt = tile / NT, nt = tile % NT;
-            if (mt >= n_mt) continue;
+        for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const int row = row_pass_base + mt * 16 + gid + (c >= 2 ? 8 : 0);
                 if (row >= R) continue;
                 const int a = row / L, l = row - a * L;
                 const int ch = nt * 8 + 2 * tig + (c & 1);
-                atomicAdd(p.out + ((size_t)(l * h + h0 + hh) * D + ch) * 3 + a, acc[hh][tp][c]);
+                atomicAdd(p.out + ((size_t)(l * h + h0 + hh) * D + ch) * 3 + a, acc[j][nt][c]);
             }
-        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -781,12 +768,9 @@ template <int D, int HGC, bool PERM>
 static int launch_table_grad_hg(const SegParams &p, int M, const char *name, cudaStream_t s) {
     const int R = 3 * p.L;
     const int Rpad = min(256, (R + 15) / 16 * 16);
-    const bool fold = p.T2 != nullptr;
-    STB200_REQUIRE(!fold || R <= 256, STB200_ERR_ARG, "folded row gradient needs a table of at most 85 rows");
-    const size_t smem = ((size_t)HGC * Rpad * kTQP + HGC * kTQ * (D + 8) + HGC * kPC + kPC + kTQ + 8 + (fold ? D * (Rpad + 4) : 0)) * sizeof(float);
+    const size_t smem = ((size_t)HGC * Rpad * kTQP + HGC * kTQ * (D + 8) + HGC * kPC + kPC + 3 * kTQ + 8) * sizeof(float);
     void (*kern)(const SegParams, int, int) =
-        fold ? table_grad_kernel<D, HGC, PERM, false, true>
-             : (R <= 256 ? table_grad_kernel<D, HGC, PERM, false, false> : table_grad_kernel<D, HGC, PERM, true, false>);
+        R <= 256 ? table_grad_kernel<D, HGC, PERM, false> : table_grad_kernel<D, HGC, PERM, true>;
     if (int rc = prep_smem(kern, smem)) return rc;
     const int tiles = (p.N + kTQ - 1) / kTQ;
     const int groups = p.h / HGC;
@@ -794,7 +778,7 @@ static int launch_table_grad_hg(const SegParams &p, int M, const char *name, cud
     static const int tg_waves = max(1, getenv("STB200_TG_WAVES") ? atoi(getenv("STB200_TG_WAVES")) : 1);
     const int gx = max(1, min(tiles, (kNumSMs * ctas_per_sm * tg_waves + groups - 1) / groups));
     for (int pass = 0; pass < R; pass += 256) {
-        KernelScope ks(name, seg_bytes(p, D, M, true, false, true, false, PERM, 1, false) - 4.0 * p.N * p.h * D + (fold ? 8.0 * p.N * p.h * D : 0.0), s);
+        KernelScope ks(name, seg_bytes(p, D, M, true, false, true, false, PERM, 1, false) - 4.0 * p.N * p.h * D, s);
         kern<<<dim3(gx, groups), kTGThreads(HGC), smem, s>>>(p, pass, Rpad);
     }
     return check_launch(name);
@@ -804,7 +788,8 @@ template <int D, bool PERM>
 static int launch_table_grad_d(const SegParams &p, int M, const char *name, cudaStream_t s) {
     STB200_REQUIRE(p.L <= 256, STB200_ERR_ARG, "table length %d > 256 not supported by the table-gradient kernel", p.L);
     constexpr int cap = D == 16 ? 3 : 2;   // heads per CTA: shared-memory histograms and 2*(D/8)*4 accumulators per head
-    switch (largest_head_group(p.h, cap)) {
+    static const int env_cap = getenv("STB200_TG_HEADS") ? atoi(getenv("STB200_TG_HEADS")) : cap;   // tuning knob
+    switch (largest_head_group(p.h, max(1, min(cap, env_cap)))) {
         case 3: return launch_table_grad_hg<D, (cap >= 3 ? 3 : 1), PERM>(p, M, name, s);
         case 2: return launch_table_grad_hg<D, 2, PERM>(p, M, name, s);
         default: return launch_table_grad_hg<D, 1, PERM>(p, M, name, s);
@@ -1025,32 +1010,17 @@ int stb200_window_logits_backward(const stb200_index *ix, int h, int hdim, int L
     const int M = ix->M;
     SegParams p{};
     p.N = ix->N; p.h = h; p.L = L; p.w = grad_logits; p.rel_idx = ix->rel_idx; p.row_order = ix->row_order;
-    // Optional (STB200_FOLD_ROWGRAD=1): take the rel-pos part of grad_q / grad_k from the histograms inside the
-    // table-gradient kernels (G = W^T T on the tensor cores) instead of per-pair table look-ups.  Measured neutral on
-    // B200 at the S3DIS shapes (the look-up kernels get 2.5x faster, the table-gradient kernels 1.7x slower), so off by default.
-    static const bool fold_env = getenv("STB200_FOLD_ROWGRAD") && atoi(getenv("STB200_FOLD_ROWGRAD")) != 0;
-    const bool fold = fold_env && 3 * L <= 256;
     // grad_q = sum g * (k[i1] + Eq)                                              (overwritten)
     p.packed = ix->rel_packed; p.offsets = ix->index0_offsets; p.gather_idx = ix->index1; p.Y = k; p.Tx = table_q; p.out = grad_q;
-    if (fold) {
-        if (int rc = launch_seg_reduce<true, false, false>(hdim, p, M, "seg_reduce[logits_bwd_gq]", s)) return rc;
-    } else {
-        if (int rc = launch_seg_reduce<true, true, false>(hdim, p, M, "seg_reduce[logits_bwd_gq]", s)) return rc;
-    }
-    p.X = q; p.out = grad_table_q; p.row_order = nullptr;
-    if (fold) { p.T2 = table_q; p.out2 = grad_q; }
+    if (int rc = launch_seg_reduce<true, true, false>(hdim, p, M, "seg_reduce[logits_bwd_gq]", s)) return rc;
+    p.X = q; p.out = grad_table_q; p.row_order = ix->len_order;   // tiles of equally long rows (balance), may be null
     if (int rc = launch_table_grad<false>(hdim, p, M, "table_grad[logits_bwd_gtq]", s)) return rc;
     // grad_k = sum over incoming pairs g * (q[i0] + Ek)                           (overwritten)
-    p.T2 = nullptr; p.out2 = nullptr; p.row_order = ix->row_order;
+    p.row_order = ix->row_order;
     p.packed = ix->t_rel_packed; p.offsets = ix->t_offsets; p.pair_id = ix->t_pair; p.gather_idx = ix->t_index0;
     p.Y = q; p.Tx = table_k; p.out = grad_k; p.accumulate = 0;   // fused API: grad_k is overwritten
-    if (fold) {
-        if (int rc = launch_seg_reduce<true, false, true>(hdim, p, M, "seg_reduce_t[logits_bwd_gk]", s)) return rc;
-    } else {
-        if (int rc = launch_seg_reduce<true, true, true>(hdim, p, M, "seg_reduce_t[logits_bwd_gk]", s)) return rc;
-    }
-    p.X = k; p.out = grad_table_k; p.row_order = nullptr;
-    if (fold) { p.T2 = table_k; p.out2 = grad_k; }
+    if (int rc = launch_seg_reduce<true, true, true>(hdim, p, M, "seg_reduce_t[logits_bwd_gk]", s)) return rc;
+    p.X = k; p.out = grad_table_k; p.row_order = ix->t_len_order;
     return launch_table_grad<true>(hdim, p, M, "table_grad_t[logits_bwd_gtk]", s);
 }
 
@@ -1079,8 +1049,9 @@ int stb200_window_aggregate_backward(const stb200_index *ix, int h, int hdim, in
     p.X = grad_out; p.Y = v; p.offsets = ix->index0_offsets; p.gather_idx = ix->index1; p.Tx = table_v; p.out = grad_attn;
     if (M > 0)
         if (int rc = launch_seg_dot<true, true, false>(hdim, p, M, "seg_dot[aggregate_bwd_gattn]", s)) return rc;
-    p.w = attn; p.out = grad_table_v;
+    p.w = attn; p.out = grad_table_v; p.row_order = ix->len_order;
     if (int rc = launch_table_grad<false>(hdim, p, M, "table_grad[aggregate_bwd_gtv]", s)) return rc;
+    p.row_order = ix->row_order;
     p.packed = nullptr; p.Y = grad_out; p.offsets = ix->t_offsets; p.pair_id = ix->t_pair; p.gather_idx = ix->t_index0;
     p.out = grad_v; p.accumulate = 0;   // fused API: grad_v is overwritten
     return launch_seg_reduce<true, false, true>(hdim, p, M, "seg_reduce_t[aggregate_bwd_gv]", s);

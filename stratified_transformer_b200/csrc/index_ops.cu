@@ -49,7 +49,24 @@ __global__ void pack_rel_kernel(int M, int L, const int *__restrict__ rel_idx, c
     }
 }
 
+// keys[i] = pair count of row r_i, vals[i] = r_i, with r_i = base_order ? base_order[i] : i
+__global__ void row_length_keys_kernel(int N, const int *__restrict__ offsets, const int *__restrict__ base_order,
+                                       int *__restrict__ keys, int *__restrict__ vals) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        const int r = base_order ? __ldg(base_order + i) : i;
+        keys[i] = __ldg(offsets + r + 1) - __ldg(offsets + r);
+        vals[i] = r;
+    }
+}
+
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static size_t length_sort_temp_bytes(int N) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const int *)nullptr, (int *)nullptr, (const int *)nullptr,
+                                    (int *)nullptr, N, 0, 32);
+    return bytes;
+}
 
 static int key_bits(int N) {
     int b = 1;
@@ -79,6 +96,36 @@ int stb200_pack_rel(int M, int L, const int *rel_idx, const int *perm, unsigned 
         pack_rel_kernel<<<max(1, min((M + 255) / 256, kNumSMs * 8)), 256, 0, (cudaStream_t)stream>>>(M, L, rel_idx, perm, out);
     }
     return check_launch("pack_rel");
+}
+
+size_t stb200_length_order_workspace_bytes(int N) {
+    if (N <= 0) return 256;
+    return 3 * align256((size_t)N * sizeof(int)) + align256(length_sort_temp_bytes(N)) + 256;
+}
+
+int stb200_length_order(int N, const int *offsets, const int *base_order, int *order, void *workspace,
+                        size_t workspace_bytes, void *stream) {
+    STB200_REQUIRE(N >= 0, STB200_ERR_ARG, "bad size");
+    if (N == 0) return STB200_OK;
+    STB200_REQUIRE(offsets && order && workspace, STB200_ERR_ARG, "null pointer");
+    STB200_REQUIRE(workspace_bytes >= stb200_length_order_workspace_bytes(N), STB200_ERR_WORKSPACE,
+                   "workspace too small: %zu < %zu", workspace_bytes, stb200_length_order_workspace_bytes(N));
+    cudaStream_t s = (cudaStream_t)stream;
+    char *ws = (char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    const size_t ni = align256((size_t)N * sizeof(int));
+    int *keys = (int *)ws, *vals = (int *)(ws + ni), *keys_out = (int *)(ws + 2 * ni);
+    void *tmp = ws + 3 * ni;
+    size_t tmp_bytes = length_sort_temp_bytes(N);
+    KernelScope ks("length_order", 4.0 * (N + 1) + 4.0 * N * (base_order ? 2 : 1), s);
+    count_launch(1);
+    row_length_keys_kernel<<<max(1, min((N + 255) / 256, kNumSMs * 8)), 256, 0, s>>>(N, offsets, base_order, keys, vals);
+    // stable: rows of equal length stay in base order (window order when the pair builder's row_order is passed)
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_out, vals, order, N, 0, 32, s);
+    if (e != cudaSuccess) {
+        set_error("cub radix sort: %s", cudaGetErrorString(e));
+        return STB200_ERR_CUDA;
+    }
+    return check_launch("length_order");
 }
 
 size_t stb200_transpose_csr_workspace_bytes(int N, int M) {

@@ -9,6 +9,7 @@ The reference rebuilds the pair list for every block although only two distinct 
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 
 import torch
@@ -37,6 +38,7 @@ class PairIndex:
     _fused: tuple | None = field(default=None, repr=False)   # (flags u8 [n_win], fallback_rows i32 [count])
     _tcsr: ext.TransposedCSR | None = field(default=None, repr=False)
     _packed: dict = field(default_factory=dict, repr=False)   # L -> (rel_packed, t_rel_packed | None)
+    _len_orders: tuple | None = field(default=None, repr=False)   # (queries by pair count, keys by incoming pair count)
 
     @property
     def N(self) -> int:
@@ -71,6 +73,22 @@ class PairIndex:
                    out.data_ptr(), _stream())
         return out
 
+    def _length_order(self, offsets: torch.Tensor) -> torch.Tensor:
+        lib = _cabi.load()
+        nbytes = lib.stb200_length_order_workspace_bytes(self.N)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=offsets.device)
+        out = torch.empty(self.N, dtype=torch.int32, device=offsets.device)
+        _cabi.call("stb200_length_order", self.N, offsets.data_ptr(), None if self.row_order is None else self.row_order.data_ptr(),
+                   out.data_ptr(), ws.data_ptr(), nbytes, _stream())
+        return out
+
+    @property
+    def len_orders(self):
+        """(queries, keys) sorted by pair count: tiles of equally long rows for the table-gradient kernels (backward only)"""
+        if self._len_orders is None:
+            self._len_orders = (self._length_order(self.index_0_offsets), self._length_order(self.tcsr.t_offsets))
+        return self._len_orders
+
     def c_struct(self, L: int, backward: bool = False) -> "_cabi.IndexStruct":
         """`stb200_index` for the fused entry points; packs the rel-pos bins on first use (per table length)."""
         ent = self._packed.get(L)
@@ -81,11 +99,14 @@ class PairIndex:
             ent[1] = self._pack(L, self.tcsr.t_pair)
         st = _cabi.IndexStruct(self.N, self.M, self.index_0_offsets.data_ptr(), self.index_1.data_ptr(),
                                self.rel_idx.data_ptr(), None, None, None, ent[0].data_ptr(), None,
-                               None if self.row_order is None else self.row_order.data_ptr())
+                               None if self.row_order is None else self.row_order.data_ptr(), None, None)
         if backward:
             t = self.tcsr
             st.t_offsets, st.t_pair, st.t_index0 = t.t_offsets.data_ptr(), t.t_pair.data_ptr(), t.t_index0.data_ptr()
             st.t_rel_packed = ent[1].data_ptr()
+            if self.N and not os.environ.get("STB200_NO_LEN_ORDER"):   # (knob for A/B measurements)
+                lo = self.len_orders
+                st.len_order, st.t_len_order = lo[0].data_ptr(), lo[1].data_ptr()
         return st
 
 
@@ -264,6 +285,8 @@ def record_stream(li: "LayerIndex", stream) -> None:
             ts += [pi._tcsr.t_offsets, pi._tcsr.t_pair, pi._tcsr.t_index0]
         for a, b in pi._packed.values():
             ts += [a, b]
+        if pi._len_orders is not None:
+            ts += list(pi._len_orders)
         for t in ts:
             if t is not None:
                 t.record_stream(stream)

@@ -259,3 +259,18 @@ def test_window_attention_under_autocast(golden_dir):
     assert out.dtype == torch.bfloat16 and feats.grad is not None and torch.isfinite(feats.grad).all()
     assert (out.float() - ref).abs().max() < 0.05 * ref.abs().max()
     assert mod.relative_pos_query_table.grad.dtype == torch.float32
+
+
+def test_length_order_is_a_stable_sort_by_pair_count(golden_dir):
+    """stb200_length_order: a permutation of the rows, non-decreasing pair count, ties in base (window) order."""
+    g = np.load(os.path.join(golden_dir, "index_s3dis_small.npz"))
+    pi = build(g["xyz"], g["offset"], float(g["window_size"]), float(g["quant_size"]), g["downsample_idx"], 1)
+    off = pi.index_0_offsets.cpu().numpy().astype(np.int64)
+    lens = off[1:] - off[:-1]
+    base = pi.row_order.cpu().numpy()
+    want = base[np.argsort(lens[base], kind="stable")]
+    q_order, k_order = pi.len_orders
+    assert np.array_equal(q_order.cpu().numpy(), want)
+    t_off = pi.tcsr.t_offsets.cpu().numpy().astype(np.int64)
+    t_lens = t_off[1:] - t_off[:-1]
+    assert np.array_equal(k_order.cpu().numpy(), base[np.argsort(t_lens[base], kind="stable")])

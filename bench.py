@@ -261,9 +261,11 @@ def device_step(levels, grads_out, geo=None, no_fused=True):
             gs = torch.empty(M, h, device=dev)
             ext.segment_softmax_backward_cuda(N, M, h, p, gp, off, gs)
             gq = torch.empty_like(q); gk = torch.empty_like(k); gtq = torch.zeros_like(tq); gtk = torch.zeros_like(tk)
-            _cabi.call("stb200_window_logits_backward", ctypes.byref(ix), h, HEAD_DIM, L, gs.data_ptr(), q.data_ptr(),
+            ws = torch.empty(M * h + 64, device=dev)   # scratch: grad rows in transposed order (see include/stb200.h)
+            wsb = 0 if os.environ.get("STB200_NO_PERMUTE_WS") else ws.numel() * 4
+            _cabi.call("stb200_window_logits_backward_ws", ctypes.byref(ix), h, HEAD_DIM, L, gs.data_ptr(), q.data_ptr(),
                        k.data_ptr(), tq.data_ptr(), tk.data_ptr(), gq.data_ptr(), gk.data_ptr(), gtq.data_ptr(),
-                       gtk.data_ptr(), stream)
+                       gtk.data_ptr(), ws.data_ptr(), wsb, stream)
             grads_out.append((gtq, gtk, gtv))
     return grads_out
 

@@ -223,6 +223,13 @@ int stb200_window_logits_forward(const stb200_index *ix, int h, int hdim, int L,
 int stb200_window_logits_backward(const stb200_index *ix, int h, int hdim, int L, const float *grad_logits,
                                   const float *q, const float *k, const float *table_q, const float *table_k,
                                   float *grad_q, float *grad_k, float *grad_table_q, float *grad_table_k, void *stream);
+/* Same, with scratch space: when `workspace` holds stb200_window_logits_backward_workspace_bytes(M, h) bytes, grad_logits
+ * is first brought into transposed-CSR order so the two key-side kernels stream it instead of gathering through t_pair. */
+size_t stb200_window_logits_backward_workspace_bytes(int M, int h);
+int stb200_window_logits_backward_ws(const stb200_index *ix, int h, int hdim, int L, const float *grad_logits,
+                                     const float *q, const float *k, const float *table_q, const float *table_k,
+                                     float *grad_q, float *grad_k, float *grad_table_q, float *grad_table_k,
+                                     void *workspace, size_t workspace_bytes, void *stream);
 int stb200_window_aggregate_forward(const stb200_index *ix, int h, int hdim, int L, const float *attn, const float *v,
                                     const float *table_v, float *output, void *stream);
 int stb200_window_aggregate_backward(const stb200_index *ix, int h, int hdim, int L, const float *grad_out,

@@ -51,6 +51,7 @@ _SIGNATURES = {
     "stb200_pack_rel": [_c_int, _c_int, P, P, P, P],
     "stb200_window_logits_forward": [_IX, _c_int, _c_int, _c_int] + [P] * 6,
     "stb200_window_logits_backward": [_IX, _c_int, _c_int, _c_int] + [P] * 10,
+    "stb200_window_logits_backward_ws": [_IX, _c_int, _c_int, _c_int] + [P] * 10 + [_c_size_t, P],
     "stb200_window_aggregate_forward": [_IX, _c_int, _c_int, _c_int] + [P] * 5,
     "stb200_window_aggregate_backward": [_IX, _c_int, _c_int, _c_int] + [P] * 8,
     "stb200_window_logits_forward_bf16": [_IX, _c_int, _c_int, _c_int] + [P] * 6,
@@ -67,6 +68,7 @@ _RESTYPES = {
     "stb200_version": (_c_int, []),
     "stb200_transpose_csr_workspace_bytes": (_c_size_t, [_c_int, _c_int]),
     "stb200_length_order_workspace_bytes": (_c_size_t, [_c_int]),
+    "stb200_window_logits_backward_workspace_bytes": (_c_size_t, [_c_int, _c_int]),
     "stb200_pair_builder_workspace_bytes": (_c_size_t, [_c_int]),
     "stb200_fused_max_keys": (_c_int, []),
     "stb200_profile_enable": (None, [_c_int]),

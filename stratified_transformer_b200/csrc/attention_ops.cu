@@ -20,6 +20,7 @@
 //   * table gradients use  gT[l,h,c,a] = sum_n X[n,h,c] * W_a[n,l,h],  W_a[n,l,h] = sum_{m in seg(n), r[m,a]=l} w[m,h]:
 //     a per-row histogram (3 scalar adds per pair-head instead of 3*d atomics) followed by a register-tiled
 //     fp32 outer-product accumulation; one flush of red.global.add per CTA at the end.
+#include <algorithm>
 #include <cstdlib>
 
 #include <cub/cub.cuh>
@@ -46,6 +47,7 @@ struct SegParams {
     const unsigned *packed; // optional: the three bins of each segment slot packed 10 bits each (replaces rel_idx)
     float *out;
     int accumulate;
+    int w_by_slot;          // PERM kernels: w is already in segment-slot (transposed) order, index it by slot instead of pair id
 };
 
 // Copy one head group of a [L,h,D,3] table into shared memory as [axis][l][hh][copy][c].
@@ -210,7 +212,8 @@ __global__ void __launch_bounds__(kMaxSegThreads) seg_reduce_kernel(const SegPar
             for (int c0 = start; c0 < end; c0 += kWarp) {
                 const int cnt = min(kWarp, end - c0);
                 const int tl = c0 + min(lane, cnt - 1);
-                const int m_l = PERM ? ld_stream(p.pair_id + tl) : tl;
+                const bool need_m = PERM && !(p.w_by_slot && (!HAS_T || p.packed));
+                const int m_l = need_m ? ld_stream(p.pair_id + tl) : tl;
                 const int j_l = HAS_Y ? ld_stream(p.gather_idx + tl) : 0;
                 unsigned pk_l = 0;
                 if (HAS_T) pk_l = p.packed ? __ldg(p.packed + tl) : pack_bins(p.rel_idx + 3 * (size_t)m_l, L);
@@ -224,13 +227,14 @@ __global__ void __launch_bounds__(kMaxSegThreads) seg_reduce_kernel(const SegPar
                         const int pl = s0 + u * NS + slot;
                         act[u] = pl < cnt;
                         const int pc = act[u] ? pl : cnt - 1;
-                        const int m = PERM ? __shfl_sync(0xffffffffu, m_l, pc) : c0 + pc;
+                        const int m = need_m ? __shfl_sync(0xffffffffu, m_l, pc) : c0 + pc;
+                        const int mw = p.w_by_slot ? c0 + pc : m;
                         const int j = HAS_Y ? __shfl_sync(0xffffffffu, j_l, pc) : 0;
                         const unsigned pk = HAS_T ? __shfl_sync(0xffffffffu, pk_l, pc) : 0u;
                         const int r0 = pk & 0x3ff, r1 = (pk >> 10) & 0x3ff, r2 = pk >> 20;
 #pragma unroll
                         for (int hh = 0; hh < HG; ++hh) {
-                            wv[u][hh] = act[u] ? ld_stream(p.w + (size_t)m * h + h0 + hh) : 0.f;
+                            wv[u][hh] = act[u] ? ld_stream(p.w + (size_t)mw * h + h0 + hh) : 0.f;
                             val[u][hh] = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (HAS_Y) val[u][hh] = ld_row4(p.Y + (size_t)j * C + (h0 + hh) * D + 4 * g);
                             if (HAS_T) val[u][hh] = f4_add(table_sum4<D, HG, kReduceTableCopies<D>>(ts, L, r0, r1, r2, hh, gc), val[u][hh]);
@@ -371,7 +375,8 @@ __global__ void __launch_bounds__(kTGThreads(HGC), (D == 16 ? 2 : 1)) table_grad
                 for (int step = kTQ / 2; step; step >>= 1)
                     if (soff[t + step] <= li) t += step;
                 const int gpos = gst[t] + (li - soff[t]);
-                const int m = PERM ? __ldg(p.pair_id + gpos) : gpos;
+                const int m = PERM && !(p.w_by_slot && p.packed) ? __ldg(p.pair_id + gpos) : gpos;
+                const int mw = p.w_by_slot ? gpos : m;
                 if (p.packed) {
                     const unsigned q = __ldg(p.packed + gpos);   // 10-bit fields -> 8-bit fields
                     pk[i] = (q & 0xffu) | (((q >> 10) & 0xffu) << 8) | (((q >> 20) & 0xffu) << 16);
@@ -382,7 +387,7 @@ __global__ void __launch_bounds__(kTGThreads(HGC), (D == 16 ? 2 : 1)) table_grad
                     pk[i] = r0 | (r1 << 8) | (r2 << 16);
                 }
 #pragma unroll
-                for (int hh = 0; hh < HGC; ++hh) sw[hh * kPC + i] = __ldg(p.w + (size_t)m * h + h0 + hh);
+                for (int hh = 0; hh < HGC; ++hh) sw[hh * kPC + i] = __ldg(p.w + (size_t)mw * h + h0 + hh);
             }
             __syncthreads();
             for (int item = tid; item < HGC * 3 * kTQ; item += nthr) {   // one thread per (head, axis, row)
@@ -632,6 +637,16 @@ __global__ void __launch_bounds__(kThreads) segment_softmax_bwd_hp_kernel(int N,
             const size_t o = base + (size_t)i * h;
             gs[o] = p[o] * (gp[o] - dot);
         }
+    }
+}
+
+// dst[t, :] = src[perm[t], :]  (rows of h floats): per-pair weights into transposed-CSR order
+__global__ void permute_rows_kernel(int M, int h, const float *__restrict__ src, const int *__restrict__ perm,
+                                    float *__restrict__ dst) {
+    const long long total = (long long)M * h;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i / h), c = (int)(i - (long long)t * h);
+        dst[i] = ld_stream(src + (size_t)__ldg(perm + t) * h + c);
     }
 }
 
@@ -1002,6 +1017,16 @@ int stb200_window_logits_forward(const stb200_index *ix, int h, int hdim, int L,
 int stb200_window_logits_backward(const stb200_index *ix, int h, int hdim, int L, const float *grad_logits,
                                   const float *q, const float *k, const float *table_q, const float *table_k,
                                   float *grad_q, float *grad_k, float *grad_table_q, float *grad_table_k, void *stream) {
+    return stb200_window_logits_backward_ws(ix, h, hdim, L, grad_logits, q, k, table_q, table_k, grad_q, grad_k, grad_table_q,
+                                            grad_table_k, nullptr, 0, stream);
+}
+
+size_t stb200_window_logits_backward_workspace_bytes(int M, int h) { return (size_t)max(M, 0) * max(h, 0) * sizeof(float) + 256; }
+
+int stb200_window_logits_backward_ws(const stb200_index *ix, int h, int hdim, int L, const float *grad_logits,
+                                     const float *q, const float *k, const float *table_q, const float *table_k,
+                                     float *grad_q, float *grad_k, float *grad_table_q, float *grad_table_k,
+                                     void *workspace, size_t workspace_bytes, void *stream) {
     if (int rc = check_index(ix, true)) return rc;
     if (int rc = check_dims(ix->N, ix->M, h, hdim)) return rc;
     STB200_REQUIRE(L > 0 && L <= 256 && grad_logits && q && k && table_q && table_k && grad_q && grad_k && grad_table_q &&
@@ -1019,6 +1044,20 @@ int stb200_window_logits_backward(const stb200_index *ix, int h, int hdim, int L
     p.row_order = ix->row_order;
     p.packed = ix->t_rel_packed; p.offsets = ix->t_offsets; p.pair_id = ix->t_pair; p.gather_idx = ix->t_index0;
     p.Y = q; p.Tx = table_k; p.out = grad_k; p.accumulate = 0;   // fused API: grad_k is overwritten
+    // Both key-side kernels read grad_logits through t_pair (12-96 B useful out of every 32 B sector fetched, and a
+    // dependent load).  With a workspace the rows are brought into transposed order once and both kernels stream them.
+    if (workspace && workspace_bytes >= stb200_window_logits_backward_workspace_bytes(M, h) && M > 0) {
+        float *wt = reinterpret_cast<float *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+        {
+            KernelScope ks("permute_rows[logits_bwd]", 8.0 * M * h + 4.0 * M, s);
+            const long long total = (long long)M * h;
+            const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16);
+            permute_rows_kernel<<<blocks, 256, 0, s>>>(M, h, grad_logits, ix->t_pair, wt);
+        }
+        if (int rc = check_launch("permute_rows")) return rc;
+        p.w = wt;
+        p.w_by_slot = 1;
+    }
     if (int rc = launch_seg_reduce<true, true, true>(hdim, p, M, "seg_reduce_t[logits_bwd_gk]", s)) return rc;
     p.X = k; p.out = grad_table_k; p.row_order = ix->t_len_order;
     return launch_table_grad<true>(hdim, p, M, "table_grad_t[logits_bwd_gtk]", s);

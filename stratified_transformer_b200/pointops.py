@@ -217,9 +217,11 @@ class WindowLogits(Function):
         grad_out = grad_out.contiguous()
         gq, gk = torch.empty_like(q), torch.empty_like(k)
         gtq, gtk = torch.zeros_like(table_q), torch.zeros_like(table_k)
-        _cabi.call("stb200_window_logits_backward", ctypes.byref(ctx.pair_index.c_struct(L, backward=True)), h, d, L,
+        ws = torch.empty(grad_out.numel() + 64, dtype=torch.float32, device=q.device)   # grad rows in transposed order
+        _cabi.call("stb200_window_logits_backward_ws", ctypes.byref(ctx.pair_index.c_struct(L, backward=True)), h, d, L,
                    grad_out.data_ptr(), q.data_ptr(), k.data_ptr(), table_q.data_ptr(), table_k.data_ptr(), gq.data_ptr(),
-                   gk.data_ptr(), gtq.data_ptr(), gtk.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                   gk.data_ptr(), gtq.data_ptr(), gtk.data_ptr(), ws.data_ptr(), ws.numel() * 4,
+                   torch.cuda.current_stream().cuda_stream)
         return gq, gk, gtq, gtk, None
 
 
@@ -319,8 +321,10 @@ class WindowAttentionFused(Function):
         pointops_cuda.segment_softmax_backward_cuda(N, pi.M, h, p, gp, pi.index_0_offsets, gs)
         gq, gk = torch.empty_like(q), torch.empty_like(k)
         gtq, gtk = torch.zeros_like(table_q), torch.zeros_like(table_k)
-        _cabi.call("stb200_window_logits_backward", ctypes.byref(ix), h, d, L, gs.data_ptr(), q.data_ptr(), k.data_ptr(),
-                   table_q.data_ptr(), table_k.data_ptr(), gq.data_ptr(), gk.data_ptr(), gtq.data_ptr(), gtk.data_ptr(), stream)
+        ws = torch.empty(gs.numel() + 64, dtype=torch.float32, device=q.device)
+        _cabi.call("stb200_window_logits_backward_ws", ctypes.byref(ix), h, d, L, gs.data_ptr(), q.data_ptr(), k.data_ptr(),
+                   table_q.data_ptr(), table_k.data_ptr(), gq.data_ptr(), gk.data_ptr(), gtq.data_ptr(), gtk.data_ptr(),
+                   ws.data_ptr(), ws.numel() * 4, stream)
         return gq, gk, gv, gtq, gtk, gtv, None
 
 

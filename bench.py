@@ -317,6 +317,8 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=dev)
 
+    if os.environ.get("STB200_MAIN_PRIORITY"):   # development knob: run the attention stream at another priority
+        torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=int(os.environ["STB200_MAIN_PRIORITY"])))
     levels, rgb = build_inputs(a, rank, dev)
     n_points = levels[0]["xyz"].shape[0]
 

@@ -308,7 +308,8 @@ class GeometryPrefetcher:
 
     def __init__(self, layer_cfgs, device=None):
         self.cfgs = layer_cfgs
-        self.side = torch.cuda.Stream(device=device)
+        # stream priority of the geometry work relative to the attention stream (0 = default, -1 = higher)
+        self.side = torch.cuda.Stream(device=device, priority=int(os.environ.get("STB200_SIDE_PRIORITY", "0")))
         self.pending = None
         self.done = None
 

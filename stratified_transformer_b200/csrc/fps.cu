@@ -26,8 +26,6 @@ namespace cg = cooperative_groups;
 namespace stb200 {
 
 constexpr int kFpsThreads = 256;   // few warps per CTA: the per-iteration exchange cost grows with the warp count
-constexpr int kMaxCluster = 16;
-
 struct __align__(16) FpsRec {
     unsigned key, rank;
     float x, y, z;
@@ -104,30 +102,60 @@ __device__ __forceinline__ int warp_argmax_lane(unsigned key, unsigned rank) {
     return __ffs(bal) - 1;
 }
 
-// One iteration, per warp (no __syncthreads, no hardware cluster barrier inside the loop):
+// Packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2 on sm_100a): two points per instruction in the distance update.
+// Each half is an IEEE round-to-nearest fp32 operation, so the results are bit-identical to the scalar sequence.
+__device__ __forceinline__ unsigned long long pack2(float a, float b) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &a, float &b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// One iteration (no hardware cluster barrier and no global load inside the loop):
 //   1. every thread updates its P running minima and keeps its best candidate;
-//   2. redux argmax in the warp; the winner's record {key, rank, x, y, z} is shuffled to lanes 0..cs-1 and lane c
-//      sends it with st.async (data + complete_tx) into slot [crank * nwarps + warp] of CTA c's inbox;
-//   3. every warp waits on its own CTA's inbox mbarrier (armed by thread 0 with expect_tx for cs * nwarps records),
-//      reduces the cs * nwarps records and continues with the global winner's coordinates.
-// Inbox and mbarrier are double-buffered: a CTA cannot run two iterations ahead of a peer because it needs that
-// peer's records of the next iteration first.
-constexpr int kMaxRecords = 512;  // cluster_size * warps per CTA
+//   2. redux argmax in the warp; lane 0 leaves the warp's record {key, rank, slot} in shared memory; ONE __syncthreads;
+//   3. warp 0 reduces the <= 32 warp records and lane c sends the CTA's winner {key, rank, x, y, z} with st.async
+//      (data + complete_tx) into slot [crank] of CTA c's inbox;
+//   4. every warp waits on its own CTA's inbox mbarrier (armed by thread 0 with expect_tx for one record per CTA),
+//      reduces the cluster_size records and continues with the global winner's coordinates.
+// Warp records, inbox and mbarrier are double-buffered by iteration parity: a CTA cannot run two iterations ahead of a
+// peer because it needs that peer's record of the next iteration first, and a warp cannot overwrite a record buffer
+// before warp 0 has read it because two __syncthreads lie in between.
+// (First version: every WARP sent its record to every CTA - no __syncthreads, but 4x the DSMEM stores and a 64-record
+// inbox scan per warp; stamps showed 535 of 2000 cycles per iteration in that scan alone.)
+constexpr int kMaxCluster = 16;
 
 template <int P, bool CLUSTER, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
 fps_kernel(const float *__restrict__ xyz, const int *__restrict__ offset, const int *__restrict__ new_offset,
            int *__restrict__ idx, int logB, int cluster_size, long long *dbg) {
     extern __shared__ float sxyz[];  // [3][P * T] coordinates of this CTA's points, for winner look-up
-    __shared__ uint4 inbox_a[2][kMaxRecords];   // key, rank, x, y
-    __shared__ float inbox_z[2][kMaxRecords];
+    __shared__ uint4 inbox_a[2][kMaxCluster];   // key, rank, x, y  - one record per CTA of the cluster
+    __shared__ float inbox_z[2][kMaxCluster];
+    __shared__ uint4 wrec[2][kWarp];            // key, rank, slot, -  - one record per warp of this CTA
     __shared__ __align__(8) unsigned long long cbar[2];
 
     const int T = blockDim.x, tid = threadIdx.x, lane = tid % kWarp, warp = tid / kWarp, nwarps = T / kWarp;
     const int crank = CLUSTER ? (int)cg::this_cluster().block_rank() : 0;
     const int scene = blockIdx.x / cluster_size;
     const int TT = T * cluster_size, gtid = crank * T + tid;
-    const int nrec = cluster_size * nwarps;
 
     const int start_n = scene ? offset[scene - 1] : 0, n = offset[scene] - start_n;
     const int start_m = scene ? new_offset[scene - 1] : 0, m = new_offset[scene] - start_m;
@@ -137,6 +165,7 @@ fps_kernel(const float *__restrict__ xyz, const int *__restrict__ offset, const 
         mbar_init(smem_u32(&cbar[1]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    constexpr int P2 = P / 2;   // point pairs handled with packed arithmetic; an odd last point stays scalar
     float px[P], py[P], pz[P], mind[P];
 #pragma unroll
     for (int u = 0; u < P; ++u) {
@@ -150,6 +179,13 @@ fps_kernel(const float *__restrict__ xyz, const int *__restrict__ offset, const 
         sxyz[1 * P * T + u * T + tid] = py[u];
         sxyz[2 * P * T + u * T + tid] = pz[u];
     }
+    unsigned long long x2[P2 > 0 ? P2 : 1], y2[P2 > 0 ? P2 : 1], z2[P2 > 0 ? P2 : 1];
+#pragma unroll
+    for (int k = 0; k < P2; ++k) {
+        x2[k] = pack2(px[2 * k], px[2 * k + 1]);
+        y2[k] = pack2(py[2 * k], py[2 * k + 1]);
+        z2[k] = pack2(pz[2 * k], pz[2 * k + 1]);
+    }
     float ox = 0.f, oy = 0.f, oz = 0.f;
     if (n > 0) {
         ox = xyz[(size_t)start_n * 3 + 0];
@@ -157,20 +193,20 @@ fps_kernel(const float *__restrict__ xyz, const int *__restrict__ offset, const 
         oz = xyz[(size_t)start_n * 3 + 2];
     }
     if (gtid == 0 && m > 0) idx[start_m] = start_n;
-    // destination of this lane's sends: slot of (this CTA, this warp) in the inbox of CTA `lane`
+    // destination of warp 0's sends: slot of this CTA in the inbox of CTA `lane`
     unsigned dst_a[2] = {0, 0}, dst_z[2] = {0, 0}, dst_bar[2] = {0, 0};
-    if (lane < cluster_size) {
+    if (warp == 0 && lane < cluster_size) {
 #pragma unroll
         for (int bf = 0; bf < 2; ++bf) {
-            dst_a[bf] = map_to_cta(smem_u32(&inbox_a[bf][crank * nwarps + warp]), (unsigned)lane);
-            dst_z[bf] = map_to_cta(smem_u32(&inbox_z[bf][crank * nwarps + warp]), (unsigned)lane);
+            dst_a[bf] = map_to_cta(smem_u32(&inbox_a[bf][crank]), (unsigned)lane);
+            dst_z[bf] = map_to_cta(smem_u32(&inbox_z[bf][crank]), (unsigned)lane);
             dst_bar[bf] = map_to_cta(smem_u32(&cbar[bf]), (unsigned)lane);
         }
     }
     __syncthreads();
     if (CLUSTER) cg::this_cluster().sync();  // barriers initialised and every CTA resident before any remote store
 
-    const unsigned tx_bytes = 20u * (unsigned)nrec;
+    const unsigned tx_bytes = 20u * (unsigned)cluster_size;
     for (int j = 1; j < m; ++j) {
         const int buf = j & 1;
         const unsigned parity = (unsigned)((j - 1) >> 1) & 1u;  // k-th use of this buffer, k = (j-1)/2
@@ -181,8 +217,26 @@ fps_kernel(const float *__restrict__ xyz, const int *__restrict__ offset, const 
         if (stamp) ds[0] = clock64();
         float best = -2.f;
         int bu = 0;
+        const unsigned long long ox2 = pack2(ox, ox), oy2 = pack2(oy, oy), oz2 = pack2(oz, oz);
 #pragma unroll
-        for (int u = 0; u < P; ++u) {
+        for (int k = 0; k < P2; ++k) {
+            const unsigned long long dx = sub2(x2[k], ox2), dy = sub2(y2[k], oy2), dz = sub2(z2[k], oz2);
+            float da, db;
+            unpack2(fma2(dz, dz, fma2(dx, dx, mul2(dy, dy))), da, db);
+            const float ma = fminf(da, mind[2 * k]), mb = fminf(db, mind[2 * k + 1]);
+            mind[2 * k] = ma;
+            mind[2 * k + 1] = mb;
+            if (ma > best) {
+                best = ma;
+                bu = 2 * k;
+            }
+            if (mb > best) {
+                best = mb;
+                bu = 2 * k + 1;
+            }
+        }
+        if (P & 1) {
+            constexpr int u = P - 1;
             const float dx = __fsub_rn(px[u], ox), dy = __fsub_rn(py[u], oy), dz = __fsub_rn(pz[u], oz);
             const float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
             const float d2 = fminf(d, mind[u]);
@@ -198,9 +252,14 @@ fps_kernel(const float *__restrict__ xyz, const int *__restrict__ offset, const 
         if (stamp) ds[1] = clock64();
         {
             const int src = warp_argmax_lane(key, rank);
-            const int slot = bu * T + tid;
-            const unsigned wk = __shfl_sync(0xffffffffu, key, src), wr = __shfl_sync(0xffffffffu, rank, src);
-            const int wslot = __shfl_sync(0xffffffffu, slot, src);
+            if (lane == src) wrec[buf][warp] = make_uint4(key, rank, (unsigned)(bu * T + tid), 0u);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const uint4 r = lane < nwarps ? wrec[buf][lane] : make_uint4(0u, 0xffffffffu, 0u, 0u);
+            const int src = warp_argmax_lane(r.x, r.y);
+            const unsigned wk = __shfl_sync(0xffffffffu, r.x, src), wr = __shfl_sync(0xffffffffu, r.y, src);
+            const int wslot = (int)__shfl_sync(0xffffffffu, r.z, src);
             if (lane < cluster_size) {
                 const float wx = sxyz[0 * P * T + wslot], wy = sxyz[1 * P * T + wslot], wz = sxyz[2 * P * T + wslot];
                 st_async_v4(dst_a[buf], wk, wr, __float_as_uint(wx), __float_as_uint(wy), dst_bar[buf]);
@@ -211,23 +270,13 @@ fps_kernel(const float *__restrict__ xyz, const int *__restrict__ offset, const 
         mbar_wait(smem_u32(&cbar[buf]), parity);
         if (stamp) ds[3] = clock64();
         {
-            unsigned bk = 0u, br = 0xffffffffu;
-            int bi = 0;
-            for (int r = lane; r < nrec; r += kWarp) {
-                const uint4 a = inbox_a[buf][r];
-                if (a.x > bk || (a.x == bk && a.y < br)) {
-                    bk = a.x;
-                    br = a.y;
-                    bi = r;
-                }
-            }
-            const int src = warp_argmax_lane(bk, br);
-            const int wi = __shfl_sync(0xffffffffu, bi, src);
-            const uint4 a = inbox_a[buf][wi];
-            ox = __uint_as_float(a.z);
-            oy = __uint_as_float(a.w);
-            oz = inbox_z[buf][wi];
-            if (gtid == 0) idx[start_m + j] = start_n + fps_unrank(a.y, logB);
+            const uint4 a = lane < cluster_size ? inbox_a[buf][lane] : make_uint4(0u, 0xffffffffu, 0u, 0u);
+            const int src = warp_argmax_lane(a.x, a.y);
+            const uint4 w = inbox_a[buf][src];
+            ox = __uint_as_float(w.z);
+            oy = __uint_as_float(w.w);
+            oz = inbox_z[buf][src];
+            if (gtid == 0) idx[start_m + j] = start_n + fps_unrank(w.y, logB);
         }
         if (stamp) ds[4] = clock64();
     }
@@ -358,9 +407,10 @@ extern "C" int stb200_furthestsampling(int b, int n, const float *xyz, const int
     const int logB = ref_block_log2(n);
     // cluster size: as many CTAs per scene as keep all scenes co-resident (148 SMs), but never more threads than points
     // tuning overrides (development): STB200_FPS_CLUSTER caps the cluster size, STB200_FPS_THREADS sets the CTA size
-    // large scenes: 128-thread CTAs in clusters of 16 (measured faster than 256 x 8); otherwise 256 threads
+    // large scenes: 128-thread CTAs (one warp per scheduler, 40 points per thread) measured faster than 256 x 20
     const int threads = env_int("STB200_FPS_THREADS", n > 16 * kFpsThreads * 12 ? 128 : kFpsThreads);
-    const int per_thread = env_int("STB200_FPS_POINTS", 10);   // target points per thread when choosing the cluster size
+    // target points per thread when choosing the cluster size: small scenes spread over more CTAs (measured)
+    const int per_thread = env_int("STB200_FPS_POINTS", n > 8192 ? 10 : 3);
     int cs = 1;
     while (cs < env_int("STB200_FPS_CLUSTER", kMaxCluster) && b * cs * 2 <= kNumSMs && cs * threads * per_thread < n) cs <<= 1;
     for (; cs >= 1; cs >>= 1) {

@@ -211,7 +211,8 @@ typedef struct stb200_index {
                                      lane per row: rows of equal length keep all lanes busy */
 } stb200_index;
 
-/* order[] = the rows listed in base_order (NULL: 0..N-1) stably sorted by pair count offsets[r+1]-offsets[r]. */
+/* order[] = the rows listed in base_order (NULL: 0..N-1) stably sorted by pair count offsets[r+1]-offsets[r]
+ * (counts above 65535 compare equal: the order is a balance hint, any permutation is valid input for the kernels). */
 size_t stb200_length_order_workspace_bytes(int N);
 int stb200_length_order(int N, const int *offsets, const int *base_order, int *order, void *workspace,
                         size_t workspace_bytes, void *stream);

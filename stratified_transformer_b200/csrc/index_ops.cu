@@ -49,12 +49,14 @@ __global__ void pack_rel_kernel(int M, int L, const int *__restrict__ rel_idx, c
     }
 }
 
-// keys[i] = pair count of row r_i, vals[i] = r_i, with r_i = base_order ? base_order[i] : i
+constexpr int kLengthKeyBits = 16, kLengthKeyMax = (1 << kLengthKeyBits) - 1;   // two radix passes
+
+// keys[i] = pair count of row r_i (clamped), vals[i] = r_i, with r_i = base_order ? base_order[i] : i
 __global__ void row_length_keys_kernel(int N, const int *__restrict__ offsets, const int *__restrict__ base_order,
                                        int *__restrict__ keys, int *__restrict__ vals) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
         const int r = base_order ? __ldg(base_order + i) : i;
-        keys[i] = __ldg(offsets + r + 1) - __ldg(offsets + r);
+        keys[i] = min(__ldg(offsets + r + 1) - __ldg(offsets + r), kLengthKeyMax);   // a balance hint: longer rows may tie
         vals[i] = r;
     }
 }
@@ -64,7 +66,7 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 static size_t length_sort_temp_bytes(int N) {
     size_t bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const int *)nullptr, (int *)nullptr, (const int *)nullptr,
-                                    (int *)nullptr, N, 0, 32);
+                                    (int *)nullptr, N, 0, kLengthKeyBits);
     return bytes;
 }
 
@@ -120,7 +122,7 @@ int stb200_length_order(int N, const int *offsets, const int *base_order, int *o
     count_launch(1);
     row_length_keys_kernel<<<max(1, min((N + 255) / 256, kNumSMs * 8)), 256, 0, s>>>(N, offsets, base_order, keys, vals);
     // stable: rows of equal length stay in base order (window order when the pair builder's row_order is passed)
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_out, vals, order, N, 0, 32, s);
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_out, vals, order, N, 0, kLengthKeyBits, s);
     if (e != cudaSuccess) {
         set_error("cub radix sort: %s", cudaGetErrorString(e));
         return STB200_ERR_CUDA;

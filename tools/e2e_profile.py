@@ -13,7 +13,9 @@ feat6 = torch.cat([rgb, levels[0]["xyz"].cpu()], 1).to(dev)
 xyzs = [lv["xyz"] for lv in levels]; offs = [lv["offset"] for lv in levels]; subs = [None] + [lv["sub_idx"] for lv in levels[1:]]
 def step():
     model.zero_grad(set_to_none=True)
-    loss = model(feat6, xyzs, offs, subs); loss.backward(); return float(loss.item())
+    with torch.autocast("cuda", dtype=torch.bfloat16):   # as bench.py's e2e leg
+        loss = model(feat6, xyzs, offs, subs)
+    loss.backward(); return float(loss.item())
 for _ in range(2): step()
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:

@@ -540,8 +540,10 @@ __global__ void __launch_bounds__(kThreads) segment_softmax_bwd_kernel(int N, in
 // a stride-h walk per head.  Values of the first kSoftCacheHP steps stay in registers.
 constexpr int kSoftCacheHP = 8;
 
-template <int HP>
-__global__ void __launch_bounds__(kThreads) segment_softmax_fwd_hp_kernel(int N, int h, const float *__restrict__ a,
+// kSoftRows rows per warp and step: their loads are issued together, which doubles the bytes in flight per warp (the
+// kernels are latency-bound streams: a row is only ~100 floats and sits behind a dependent offsets load).
+template <int HP, int R, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) segment_softmax_fwd_hp_kernel(int N, int h, const float *__restrict__ a,
                                                                           const float *__restrict__ b,
                                                                           const int *__restrict__ offsets,
                                                                           float *__restrict__ p,
@@ -550,58 +552,75 @@ __global__ void __launch_bounds__(kThreads) segment_softmax_fwd_hp_kernel(int N,
     const int lane = threadIdx.x % kWarp, hd = lane % HP, slot = lane / HP;
     const bool on = hd < h;
     const int wid = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp, nw = gridDim.x * blockDim.x / kWarp;
-    for (int nn = wid; nn < N; nn += nw) {
-        const int n = rows ? __ldg(rows + nn) : nn;
-        const int start = __ldg(offsets + n), len = __ldg(offsets + n + 1) - start;
-        if (len <= 0) continue;
-        const size_t base = (size_t)start * h + hd;
-        float v[kSoftCacheHP];
-        float mx = -INFINITY;
+    for (int nn = wid; nn < N; nn += nw * R) {
+        int len[R];
+        size_t base[R];
 #pragma unroll
-        for (int u = 0; u < kSoftCacheHP; ++u) {
-            const int i = slot + u * SL;
-            v[u] = -INFINITY;
-            if (on && i < len) {
-                v[u] = a[base + (size_t)i * h];
-                if (b) v[u] += b[base + (size_t)i * h];
+        for (int r = 0; r < R; ++r) {
+            const int row = nn + r * nw;
+            int start = 0;
+            len[r] = 0;
+            if (row < N) {
+                const int n = rows ? __ldg(rows + row) : row;
+                start = __ldg(offsets + n);
+                len[r] = __ldg(offsets + n + 1) - start;
             }
-            mx = fmaxf(mx, v[u]);
+            base[r] = (size_t)start * h + hd;
         }
-        for (int i = slot + kSoftCacheHP * SL; on && i < len; i += SL) {
-            float s = a[base + (size_t)i * h];
-            if (b) s += b[base + (size_t)i * h];
-            mx = fmaxf(mx, s);
+        float v[R][kSoftCacheHP], mx[R], sum[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            mx[r] = -INFINITY;
+#pragma unroll
+            for (int u = 0; u < kSoftCacheHP; ++u) {
+                const int i = slot + u * SL;
+                v[r][u] = -INFINITY;
+                if (on && i < len[r]) {
+                    v[r][u] = a[base[r] + (size_t)i * h];
+                    if (b) v[r][u] += b[base[r] + (size_t)i * h];
+                }
+            }
         }
 #pragma unroll
-        for (int o = HP; o < kWarp; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        float sum = 0.f;
+        for (int r = 0; r < R; ++r) {
 #pragma unroll
-        for (int u = 0; u < kSoftCacheHP; ++u) {
-            v[u] = (on && slot + u * SL < len) ? expf(v[u] - mx) : 0.f;
-            sum += v[u];
-        }
-        for (int i = slot + kSoftCacheHP * SL; on && i < len; i += SL) {
-            float s = a[base + (size_t)i * h];
-            if (b) s += b[base + (size_t)i * h];
-            sum += expf(s - mx);
-        }
+            for (int u = 0; u < kSoftCacheHP; ++u) mx[r] = fmaxf(mx[r], v[r][u]);
+            for (int i = slot + kSoftCacheHP * SL; on && i < len[r]; i += SL) {
+                float s = a[base[r] + (size_t)i * h];
+                if (b) s += b[base[r] + (size_t)i * h];
+                mx[r] = fmaxf(mx[r], s);
+            }
 #pragma unroll
-        for (int o = HP; o < kWarp; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            for (int o = HP; o < kWarp; o <<= 1) mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], o));
+            sum[r] = 0.f;
 #pragma unroll
-        for (int u = 0; u < kSoftCacheHP; ++u) {
-            const int i = slot + u * SL;
-            if (on && i < len) p[base + (size_t)i * h] = v[u] / sum;
-        }
-        for (int i = slot + kSoftCacheHP * SL; on && i < len; i += SL) {
-            float s = a[base + (size_t)i * h];
-            if (b) s += b[base + (size_t)i * h];
-            p[base + (size_t)i * h] = expf(s - mx) / sum;
+            for (int u = 0; u < kSoftCacheHP; ++u) {
+                v[r][u] = (on && slot + u * SL < len[r]) ? expf(v[r][u] - mx[r]) : 0.f;
+                sum[r] += v[r][u];
+            }
+            for (int i = slot + kSoftCacheHP * SL; on && i < len[r]; i += SL) {
+                float s = a[base[r] + (size_t)i * h];
+                if (b) s += b[base[r] + (size_t)i * h];
+                sum[r] += expf(s - mx[r]);
+            }
+#pragma unroll
+            for (int o = HP; o < kWarp; o <<= 1) sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], o);
+#pragma unroll
+            for (int u = 0; u < kSoftCacheHP; ++u) {
+                const int i = slot + u * SL;
+                if (on && i < len[r]) p[base[r] + (size_t)i * h] = v[r][u] / sum[r];
+            }
+            for (int i = slot + kSoftCacheHP * SL; on && i < len[r]; i += SL) {
+                float s = a[base[r] + (size_t)i * h];
+                if (b) s += b[base[r] + (size_t)i * h];
+                p[base[r] + (size_t)i * h] = expf(s - mx[r]) / sum[r];
+            }
         }
     }
 }
 
-template <int HP>
-__global__ void __launch_bounds__(kThreads) segment_softmax_bwd_hp_kernel(int N, int h, const float *__restrict__ p,
+template <int HP, int R, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) segment_softmax_bwd_hp_kernel(int N, int h, const float *__restrict__ p,
                                                                           const float *__restrict__ gp,
                                                                           const int *__restrict__ offsets,
                                                                           float *__restrict__ gs) {
@@ -609,33 +628,50 @@ __global__ void __launch_bounds__(kThreads) segment_softmax_bwd_hp_kernel(int N,
     const int lane = threadIdx.x % kWarp, hd = lane % HP, slot = lane / HP;
     const bool on = hd < h;
     const int wid = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp, nw = gridDim.x * blockDim.x / kWarp;
-    for (int n = wid; n < N; n += nw) {
-        const int start = __ldg(offsets + n), len = __ldg(offsets + n + 1) - start;
-        if (len <= 0) continue;
-        const size_t base = (size_t)start * h + hd;
-        float pv[kSoftCacheHP], gv[kSoftCacheHP];
-        float dot = 0.f;
+    for (int nn = wid; nn < N; nn += nw * R) {
+        int len[R];
+        size_t base[R];
 #pragma unroll
-        for (int u = 0; u < kSoftCacheHP; ++u) {
-            const int i = slot + u * SL;
-            pv[u] = gv[u] = 0.f;
-            if (on && i < len) {
-                pv[u] = p[base + (size_t)i * h];
-                gv[u] = gp[base + (size_t)i * h];
+        for (int r = 0; r < R; ++r) {
+            const int n = nn + r * nw;
+            int start = 0;
+            len[r] = 0;
+            if (n < N) {
+                start = __ldg(offsets + n);
+                len[r] = __ldg(offsets + n + 1) - start;
             }
-            dot = fmaf(pv[u], gv[u], dot);
+            base[r] = (size_t)start * h + hd;
         }
-        for (int i = slot + kSoftCacheHP * SL; on && i < len; i += SL) dot = fmaf(p[base + (size_t)i * h], gp[base + (size_t)i * h], dot);
+        float pv[R][kSoftCacheHP], gv[R][kSoftCacheHP];
 #pragma unroll
-        for (int o = HP; o < kWarp; o <<= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int u = 0; u < kSoftCacheHP; ++u) {
-            const int i = slot + u * SL;
-            if (on && i < len) gs[base + (size_t)i * h] = pv[u] * (gv[u] - dot);
-        }
-        for (int i = slot + kSoftCacheHP * SL; on && i < len; i += SL) {
-            const size_t o = base + (size_t)i * h;
-            gs[o] = p[o] * (gp[o] - dot);
+            for (int u = 0; u < kSoftCacheHP; ++u) {
+                const int i = slot + u * SL;
+                pv[r][u] = gv[r][u] = 0.f;
+                if (on && i < len[r]) {
+                    pv[r][u] = p[base[r] + (size_t)i * h];
+                    gv[r][u] = gp[base[r] + (size_t)i * h];
+                }
+            }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float dot = 0.f;
+#pragma unroll
+            for (int u = 0; u < kSoftCacheHP; ++u) dot = fmaf(pv[r][u], gv[r][u], dot);
+            for (int i = slot + kSoftCacheHP * SL; on && i < len[r]; i += SL)
+                dot = fmaf(p[base[r] + (size_t)i * h], gp[base[r] + (size_t)i * h], dot);
+#pragma unroll
+            for (int o = HP; o < kWarp; o <<= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+#pragma unroll
+            for (int u = 0; u < kSoftCacheHP; ++u) {
+                const int i = slot + u * SL;
+                if (on && i < len[r]) gs[base[r] + (size_t)i * h] = pv[r][u] * (gv[r][u] - dot);
+            }
+            for (int i = slot + kSoftCacheHP * SL; on && i < len[r]; i += SL) {
+                const size_t o = base[r] + (size_t)i * h;
+                gs[o] = p[o] * (gp[o] - dot);
+            }
         }
     }
 }
@@ -663,6 +699,50 @@ static int seg_threads(int ntables, bool reduce = false) {
     // seg_reduce (about 100 registers per thread) does slightly better with two 256-thread CTAs, which also still fit
     // beside a resident FPS CTA of the geometry stream
     return ntables > 0 && !reduce ? 512 : kThreads;
+}
+
+// softmax launch variants: rows per warp step (R) x resident CTAs per SM (MINB); tuning knob STB200_SOFTMAX_VARIANT
+static int softmax_variant() {
+    static const int v = getenv("STB200_SOFTMAX_VARIANT") ? atoi(getenv("STB200_SOFTMAX_VARIANT")) : 0;
+    return v;
+}
+template <int HP>
+static void launch_softmax_fwd_hp1(int blocks, cudaStream_t s, int N, int h, const float *a, const float *b, const int *off,
+                                   float *p, const int *rows) {
+    switch (softmax_variant()) {
+        case 1: segment_softmax_fwd_hp_kernel<HP, 2, 4><<<blocks, kThreads, 0, s>>>(N, h, a, b, off, p, rows); break;
+        case 2: segment_softmax_fwd_hp_kernel<HP, 2, 6><<<blocks, kThreads, 0, s>>>(N, h, a, b, off, p, rows); break;
+        case 3: segment_softmax_fwd_hp_kernel<HP, 1, 8><<<blocks, kThreads, 0, s>>>(N, h, a, b, off, p, rows); break;
+        default: segment_softmax_fwd_hp_kernel<HP, 1, 1><<<blocks, kThreads, 0, s>>>(N, h, a, b, off, p, rows); break;
+    }
+}
+static void launch_softmax_fwd_hp(int blocks, cudaStream_t s, int N, int h, const float *a, const float *b, const int *off,
+                                  float *p, const int *rows = nullptr) {
+    if (h <= 1) launch_softmax_fwd_hp1<1>(blocks, s, N, h, a, b, off, p, rows);
+    else if (h <= 2) launch_softmax_fwd_hp1<2>(blocks, s, N, h, a, b, off, p, rows);
+    else if (h <= 4) launch_softmax_fwd_hp1<4>(blocks, s, N, h, a, b, off, p, rows);
+    else if (h <= 8) launch_softmax_fwd_hp1<8>(blocks, s, N, h, a, b, off, p, rows);
+    else if (h <= 16) launch_softmax_fwd_hp1<16>(blocks, s, N, h, a, b, off, p, rows);
+    else launch_softmax_fwd_hp1<32>(blocks, s, N, h, a, b, off, p, rows);
+}
+template <int HP>
+static void launch_softmax_bwd_hp1(int blocks, cudaStream_t s, int N, int h, const float *p, const float *gp, const int *off,
+                                   float *gs) {
+    switch (softmax_variant()) {
+        case 1: segment_softmax_bwd_hp_kernel<HP, 2, 4><<<blocks, kThreads, 0, s>>>(N, h, p, gp, off, gs); break;
+        case 2: segment_softmax_bwd_hp_kernel<HP, 2, 6><<<blocks, kThreads, 0, s>>>(N, h, p, gp, off, gs); break;
+        case 3: segment_softmax_bwd_hp_kernel<HP, 1, 8><<<blocks, kThreads, 0, s>>>(N, h, p, gp, off, gs); break;
+        default: segment_softmax_bwd_hp_kernel<HP, 1, 1><<<blocks, kThreads, 0, s>>>(N, h, p, gp, off, gs); break;
+    }
+}
+static void launch_softmax_bwd_hp(int blocks, cudaStream_t s, int N, int h, const float *p, const float *gp, const int *off,
+                                  float *gs) {
+    if (h <= 1) launch_softmax_bwd_hp1<1>(blocks, s, N, h, p, gp, off, gs);
+    else if (h <= 2) launch_softmax_bwd_hp1<2>(blocks, s, N, h, p, gp, off, gs);
+    else if (h <= 4) launch_softmax_bwd_hp1<4>(blocks, s, N, h, p, gp, off, gs);
+    else if (h <= 8) launch_softmax_bwd_hp1<8>(blocks, s, N, h, p, gp, off, gs);
+    else if (h <= 16) launch_softmax_bwd_hp1<16>(blocks, s, N, h, p, gp, off, gs);
+    else launch_softmax_bwd_hp1<32>(blocks, s, N, h, p, gp, off, gs);
 }
 
 // CTAs per launch = resident capacity x "waves".  More than one wave lets the hardware block scheduler rebalance when
@@ -940,12 +1020,7 @@ int stb200_segment_softmax_forward(int N, int M, int h, const float *a, const fl
     {
         KernelScope ks("segment_softmax_fwd", 4.0 * M * h * (b ? 3 : 2) + 4.0 * (N + 1), (cudaStream_t)stream);
         cudaStream_t s = (cudaStream_t)stream;
-        if (h <= 1) segment_softmax_fwd_hp_kernel<1><<<blocks, kThreads, 0, s>>>(N, h, a, b, index0_offsets, p);
-        else if (h <= 2) segment_softmax_fwd_hp_kernel<2><<<blocks, kThreads, 0, s>>>(N, h, a, b, index0_offsets, p);
-        else if (h <= 4) segment_softmax_fwd_hp_kernel<4><<<blocks, kThreads, 0, s>>>(N, h, a, b, index0_offsets, p);
-        else if (h <= 8) segment_softmax_fwd_hp_kernel<8><<<blocks, kThreads, 0, s>>>(N, h, a, b, index0_offsets, p);
-        else if (h <= 16) segment_softmax_fwd_hp_kernel<16><<<blocks, kThreads, 0, s>>>(N, h, a, b, index0_offsets, p);
-        else if (h <= 32) segment_softmax_fwd_hp_kernel<32><<<blocks, kThreads, 0, s>>>(N, h, a, b, index0_offsets, p);
+        if (h <= 32) launch_softmax_fwd_hp(blocks, s, N, h, a, b, index0_offsets, p);
         else segment_softmax_fwd_kernel<<<blocks, kThreads, 0, s>>>(N, h, a, b, index0_offsets, p);
     }
     return check_launch("segment_softmax_fwd");
@@ -960,12 +1035,7 @@ int stb200_segment_softmax_forward_rows(int n_rows, const int *rows, int h, cons
     cudaStream_t s = (cudaStream_t)stream;
     {
         KernelScope ks("segment_softmax_fwd", 0.0, s);
-        if (h <= 1) segment_softmax_fwd_hp_kernel<1><<<blocks, kThreads, 0, s>>>(n_rows, h, a, b, index0_offsets, p, rows);
-        else if (h <= 2) segment_softmax_fwd_hp_kernel<2><<<blocks, kThreads, 0, s>>>(n_rows, h, a, b, index0_offsets, p, rows);
-        else if (h <= 4) segment_softmax_fwd_hp_kernel<4><<<blocks, kThreads, 0, s>>>(n_rows, h, a, b, index0_offsets, p, rows);
-        else if (h <= 8) segment_softmax_fwd_hp_kernel<8><<<blocks, kThreads, 0, s>>>(n_rows, h, a, b, index0_offsets, p, rows);
-        else if (h <= 16) segment_softmax_fwd_hp_kernel<16><<<blocks, kThreads, 0, s>>>(n_rows, h, a, b, index0_offsets, p, rows);
-        else segment_softmax_fwd_hp_kernel<32><<<blocks, kThreads, 0, s>>>(n_rows, h, a, b, index0_offsets, p, rows);
+        if (h <= 32) launch_softmax_fwd_hp(blocks, s, n_rows, h, a, b, index0_offsets, p, rows);
     }
     return check_launch("segment_softmax_fwd_rows");
 }
@@ -979,12 +1049,7 @@ int stb200_segment_softmax_backward(int N, int M, int h, const float *p, const f
     {
         KernelScope ks("segment_softmax_bwd", 4.0 * M * h * 3 + 4.0 * (N + 1), (cudaStream_t)stream);
         cudaStream_t s = (cudaStream_t)stream;
-        if (h <= 1) segment_softmax_bwd_hp_kernel<1><<<blocks, kThreads, 0, s>>>(N, h, p, grad_p, index0_offsets, grad_s);
-        else if (h <= 2) segment_softmax_bwd_hp_kernel<2><<<blocks, kThreads, 0, s>>>(N, h, p, grad_p, index0_offsets, grad_s);
-        else if (h <= 4) segment_softmax_bwd_hp_kernel<4><<<blocks, kThreads, 0, s>>>(N, h, p, grad_p, index0_offsets, grad_s);
-        else if (h <= 8) segment_softmax_bwd_hp_kernel<8><<<blocks, kThreads, 0, s>>>(N, h, p, grad_p, index0_offsets, grad_s);
-        else if (h <= 16) segment_softmax_bwd_hp_kernel<16><<<blocks, kThreads, 0, s>>>(N, h, p, grad_p, index0_offsets, grad_s);
-        else if (h <= 32) segment_softmax_bwd_hp_kernel<32><<<blocks, kThreads, 0, s>>>(N, h, p, grad_p, index0_offsets, grad_s);
+        if (h <= 32) launch_softmax_bwd_hp(blocks, s, N, h, p, grad_p, index0_offsets, grad_s);
         else segment_softmax_bwd_kernel<<<blocks, kThreads, 0, s>>>(N, h, p, grad_p, index0_offsets, grad_s);
     }
     return check_launch("segment_softmax_bwd");

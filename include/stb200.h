@@ -43,6 +43,7 @@ extern "C" {
 const char *stb200_last_error(void);
 /* number of kernels this library launched since load (bench.py's "gpu_launches") */
 long long stb200_launch_count(void);
+/* ABI version: 100 = first release, 101 = stb200_index has len_order / t_len_order (append-only struct growth) */
 int stb200_version(void);
 /* Optional per-kernel profiler: when enabled every launch is bracketed by CUDA events on its stream.
  * stb200_profile_dump writes a JSON object {"kernel name": {"launches", "ms", "bytes"}} (bytes = algorithmic bytes

@@ -102,6 +102,8 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = restype
+    if lib.stb200_version() < 101:   # the IndexStruct mirror below needs the 101 layout (len_order / t_len_order)
+        raise Stb200Error(f"{LIB_PATH} is stale (ABI {lib.stb200_version()} < 101): rebuild it with `make -C stratified_transformer_b200/csrc`")
     _lib = lib
     return lib
 

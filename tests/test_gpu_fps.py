@@ -47,7 +47,8 @@ def test_fps_exact_vs_oracle_and_reference(sizes, ds, lattice):
         assert np.array_equal(ref, want), "oracle disagrees with the reference kernel"
 
 
-@pytest.mark.parametrize("n,spacing", [(700, 0.5), (1251, 0.25), (4000, 0.25), (5001, 0.5), (20001, 0.25)])
+@pytest.mark.parametrize("n,spacing", [(700, 0.5), (1251, 0.25), (4000, 0.25), (5001, 0.5), (20001, 0.25),
+                                       (52000, 0.125)])   # > 49152 points: 128-thread CTAs, 40 points per thread, packed pairs
 def test_fps_exact_with_massive_ties(n, spacing):
     """Coarse lattice: most distances tie exactly, so every level of the (distance, rank) reduction and the in-thread
     scan order are exercised for each launch configuration (single CTA, small / large clusters)."""

@@ -273,8 +273,9 @@ __global__ void __launch_bounds__(kMaxSegThreads) seg_reduce_kernel(const SegPar
 // The reference issues 3*d float atomics per pair-head onto the 2*9216 table addresses.  Here the sum is split
 // into a per-row histogram (3 scalar adds per pair-head, no atomics) and a dense product with the row matrix:
 //   grid = (persistent tiles of TQ rows, head groups).  Per tile:
-//     A0  stage the tile's pairs, PC at a time: packed bins + the weights of all heads of the group, one
-//         round trip to memory per chunk with every thread issuing independent loads;
+//     A0  stage pairs [c0, c0+32) of EVERY row of the tile (the rows come from a length-sorted order, so the slices
+//         are equally full): packed bins + the weights of all heads of the group, one round trip to memory per
+//         chunk with every thread issuing independent loads;
 //     A1  one thread per (head, axis, row) adds its row's weights into its private column of
 //         W[head][(axis, l)][row] in shared memory (no atomics);
 //     B   per head: C[(axis,l), c] += W^T X on the tensor cores: mma.sync m16n8k8 TF32 with the 3-term split
@@ -282,7 +283,9 @@ __global__ void __launch_bounds__(kMaxSegThreads) seg_reduce_kernel(const SegPar
 //   one red.global.add per accumulator element at the end of the CTA.
 constexpr int kTQ = 32;        // rows per tile
 constexpr int kTQP = kTQ + 4;  // pitch of W rows: conflict-free A-fragment loads
-constexpr int kPC = 1024;      // pairs staged per chunk
+constexpr int kPR = 32;         // pairs of EACH row staged per chunk (a chunk = the same slice of all 32 rows)
+constexpr int kPRP = kPR + 1;   // pitch of a row's slice: lanes = rows read conflict-free
+constexpr int kPC = kTQ * kPRP; // staged elements per chunk
 // one thread per (head, axis, row) in the histogram phase
 __host__ __device__ constexpr int kTGThreads(int hgc) { return hgc * 3 * kTQ < 128 ? 128 : hgc * 3 * kTQ; }
 
@@ -313,9 +316,9 @@ __global__ void __launch_bounds__(kTGThreads(HGC), (D == 16 ? 2 : 1)) table_grad
     const int h0 = blockIdx.y * HGC;
     float *W = reinterpret_cast<float *>(smem4);            // [HGC][Rpad][kTQP]
     float *Xs = W + HGC * Rpad * kTQP;                      // [HGC][kTQ][XP]
-    float *sw = Xs + HGC * kTQ * XP;                        // [HGC][kPC] weights
-    unsigned *pk = reinterpret_cast<unsigned *>(sw + HGC * kPC);   // [kPC] r0 | r1<<8 | r2<<16
-    int *soff = reinterpret_cast<int *>(pk + kPC);          // [kTQ + 1] staged-list offsets of the tile's rows
+    float *sw = Xs + HGC * kTQ * XP;                        // [HGC][kTQ][kPRP] weights of the staged slice
+    unsigned *pk = reinterpret_cast<unsigned *>(sw + HGC * kPC);   // [kTQ][kPRP] r0 | r1<<8 | r2<<16
+    int *soff = reinterpret_cast<int *>(pk + kPC);          // [kTQ + 1] pair counts of the tile's rows, [kTQ] = their maximum
     int *gst = soff + kTQ + 8;                              // [kTQ] where each row's pairs start in the CSR
     int *rown = gst + kTQ;                                  // [kTQ] row ids (-1 beyond N)
     static_assert(kTQ == kWarp, "the tile prologue scans the row lengths in one warp");
@@ -332,10 +335,9 @@ __global__ void __launch_bounds__(kTGThreads(HGC), (D == 16 ? 2 : 1)) table_grad
 
     for (int base_n = blockIdx.x * kTQ; base_n < p.N; base_n += gridDim.x * kTQ) {
         __syncthreads();   // previous tile fully consumed
-        // The tile's rows are row_order[base_n .. base_n+31] (or consecutive rows).  Their pair segments need not be
-        // adjacent in the CSR: soff[] is the prefix sum of the row lengths (positions inside the staged pair list),
-        // gst[] the global start of each row's segment.  With rows sorted by length (len_order) all lanes of the
-        // histogram phase below run the same number of iterations.
+        // The tile's rows are row_order[base_n .. base_n+31] (or consecutive rows); their pair segments need not be
+        // adjacent in the CSR: gst[] = where each row's segment starts, soff[] = its length, soff[kTQ] = the longest.
+        // With rows sorted by length (len_order) every lane of the histogram phase runs the same trip count.
         if (warp == 0) {
             const int r = base_n + lane;
             int n = -1, gs = 0, len = 0;
@@ -344,14 +346,9 @@ __global__ void __launch_bounds__(kTGThreads(HGC), (D == 16 ? 2 : 1)) table_grad
                 gs = __ldg(p.offsets + n);
                 len = __ldg(p.offsets + n + 1) - gs;
             }
-            int incl = len;
-#pragma unroll
-            for (int o = 1; o < kWarp; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            soff[lane] = incl - len;
-            if (lane == kWarp - 1) soff[kTQ] = incl;
+            soff[lane] = len;
+            const int mx = __reduce_max_sync(0xffffffffu, len);
+            if (lane == 0) soff[kTQ] = mx;
             gst[lane] = gs;
             rown[lane] = n;
         }
@@ -363,41 +360,40 @@ __global__ void __launch_bounds__(kTGThreads(HGC), (D == 16 ? 2 : 1)) table_grad
             const float4 v = n >= 0 ? ld_row4(p.X + ((size_t)n * h + h0 + hh) * D + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
             *reinterpret_cast<float4 *>(Xs + (hh * kTQ + t) * XP + 4 * c4) = v;
         }
-        const int m1 = soff[kTQ];
-        // ---- histograms of all heads of the group, kPC pairs at a time
-        for (int c0 = 0; c0 < m1; c0 += kPC) {
-            const int cn = min(kPC, m1 - c0);
+        const int maxlen = soff[kTQ];
+        // ---- histograms of all heads of the group; per chunk the pairs [c0, c0 + kPR) of every row are staged as
+        // slice[row][kPRP] (128 B runs of one row -> coalesced loads; pitch 33 -> conflict-free reads by lanes = rows)
+        for (int c0 = 0; c0 < maxlen; c0 += kPR) {
             if (c0 > 0) __syncthreads();   // previous chunk consumed
-            for (int i = tid; i < cn; i += nthr) {
-                const int li = c0 + i;
-                int t = 0;   // row of staged position li: the last row starting at or before it
-#pragma unroll
-                for (int step = kTQ / 2; step; step >>= 1)
-                    if (soff[t + step] <= li) t += step;
-                const int gpos = gst[t] + (li - soff[t]);
+            for (int i = tid; i < kTQ * kPR; i += nthr) {
+                const int t = i / kPR, j = i - t * kPR;
+                if (c0 + j >= soff[t]) continue;
+                const int gpos = gst[t] + c0 + j;
                 const int m = PERM && !(p.w_by_slot && p.packed) ? __ldg(p.pair_id + gpos) : gpos;
                 const int mw = p.w_by_slot ? gpos : m;
+                const int o = t * kPRP + j;
                 if (p.packed) {
                     const unsigned q = __ldg(p.packed + gpos);   // 10-bit fields -> 8-bit fields
-                    pk[i] = (q & 0xffu) | (((q >> 10) & 0xffu) << 8) | (((q >> 20) & 0xffu) << 16);
+                    pk[o] = (q & 0xffu) | (((q >> 10) & 0xffu) << 8) | (((q >> 20) & 0xffu) << 16);
                 } else {
                     const unsigned r0 = clampi(__ldg(p.rel_idx + 3 * (size_t)m + 0), L - 1);
                     const unsigned r1 = clampi(__ldg(p.rel_idx + 3 * (size_t)m + 1), L - 1);
                     const unsigned r2 = clampi(__ldg(p.rel_idx + 3 * (size_t)m + 2), L - 1);
-                    pk[i] = r0 | (r1 << 8) | (r2 << 16);
+                    pk[o] = r0 | (r1 << 8) | (r2 << 16);
                 }
 #pragma unroll
-                for (int hh = 0; hh < HGC; ++hh) sw[hh * kPC + i] = __ldg(p.w + (size_t)mw * h + h0 + hh);
+                for (int hh = 0; hh < HGC; ++hh) sw[hh * kPC + o] = __ldg(p.w + (size_t)mw * h + h0 + hh);
             }
             __syncthreads();
             for (int item = tid; item < HGC * 3 * kTQ; item += nthr) {   // one thread per (head, axis, row)
                 const int t = item % kTQ, a = (item / kTQ) % 3, hh = item / (3 * kTQ);
-                const int s = max(soff[t], c0) - c0, e = min(soff[t + 1], c0 + cn) - c0;
+                const int cnt = min(kPR, soff[t] - c0);
                 float *col = W + hh * Rpad * kTQP + t + (a * L - row_pass_base) * kTQP;
-                const float *wsrc = sw + hh * kPC;
+                const float *wsrc = sw + hh * kPC + t * kPRP;
+                const unsigned *psrc = pk + t * kPRP;
                 const int sh = 8 * a;
-                for (int i = s; i < e; ++i) {
-                    const int bin = (int)((pk[i] >> sh) & 0xffu);
+                for (int i = 0; i < cnt; ++i) {
+                    const int bin = (int)((psrc[i] >> sh) & 0xffu);
                     if (MULTI) {   // several passes over the table rows: skip bins outside this pass
                         const int row = a * L - row_pass_base + bin;
                         if (row < 0 || row >= Rp) continue;

@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libstb200.so")
+# STB200_LIB: development knob to load an alternative build of the same library (A/B measurements)
+LIB_PATH = os.environ.get("STB200_LIB") or os.path.join(_HERE, "lib", "libstb200.so")
 
 _c_int, _c_uint, _c_void_p, _c_size_t = ctypes.c_int, ctypes.c_uint, ctypes.c_void_p, ctypes.c_size_t
 P = _c_void_p

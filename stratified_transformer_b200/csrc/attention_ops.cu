@@ -333,56 +333,106 @@ __global__ void __launch_bounds__(kTGThreads(HGC), (D == 16 ? 2 : 1)) table_grad
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
 
-    for (int base_n = blockIdx.x * kTQ; base_n < p.N; base_n += gridDim.x * kTQ) {
+    // Row descriptors are fetched two tiles ahead (row id) / one tile ahead (segment start and length) by warp 0, so the
+    // row_order -> offsets -> pairs chain of dependent global loads is off the critical path of a tile.
+    constexpr int SE = (kTQ * kPR + kTGThreads(HGC) - 1) / kTGThreads(HGC);              // staged pairs per thread and chunk
+    constexpr int XE = (HGC * kTQ * (D / 4) + kTGThreads(HGC) - 1) / kTGThreads(HGC);    // X row quarters per thread
+    const int tile_stride = gridDim.x * kTQ;
+    int n_cur = -1, gs_cur = 0, len_cur = 0, n_next = -1;   // warp 0, lane = row of the tile
+    if (warp == 0) {
+        const int r = blockIdx.x * kTQ + lane, r2 = r + tile_stride;
+        if (r < p.N) {
+            n_cur = p.row_order ? __ldg(p.row_order + r) : r;
+            gs_cur = __ldg(p.offsets + n_cur);
+            len_cur = __ldg(p.offsets + n_cur + 1) - gs_cur;
+        }
+        if (r2 < p.N) n_next = p.row_order ? __ldg(p.row_order + r2) : r2;
+    }
+
+    for (int base_n = blockIdx.x * kTQ; base_n < p.N; base_n += tile_stride) {
         __syncthreads();   // previous tile fully consumed
         // The tile's rows are row_order[base_n .. base_n+31] (or consecutive rows); their pair segments need not be
         // adjacent in the CSR: gst[] = where each row's segment starts, soff[] = its length, soff[kTQ] = the longest.
         // With rows sorted by length (len_order) every lane of the histogram phase runs the same trip count.
         if (warp == 0) {
-            const int r = base_n + lane;
-            int n = -1, gs = 0, len = 0;
-            if (r < p.N) {
-                n = p.row_order ? __ldg(p.row_order + r) : r;
-                gs = __ldg(p.offsets + n);
-                len = __ldg(p.offsets + n + 1) - gs;
-            }
-            soff[lane] = len;
-            const int mx = __reduce_max_sync(0xffffffffu, len);
+            soff[lane] = len_cur;
+            const int mx = __reduce_max_sync(0xffffffffu, len_cur);
             if (lane == 0) soff[kTQ] = mx;
-            gst[lane] = gs;
-            rown[lane] = n;
+            gst[lane] = gs_cur;
+            rown[lane] = n_cur;
+            // descriptors of the next tile (consumed one iteration later) and row ids of the one after
+            n_cur = n_next;
+            gs_cur = 0;
+            len_cur = 0;
+            if (n_cur >= 0) {
+                gs_cur = __ldg(p.offsets + n_cur);
+                len_cur = __ldg(p.offsets + n_cur + 1) - gs_cur;
+            }
+            const int r2 = base_n + 2 * tile_stride + lane;
+            n_next = r2 < p.N ? (p.row_order ? __ldg(p.row_order + r2) : r2) : -1;
         }
         for (int i = tid; i < HGC * Rpad * kTQP / 4; i += nthr) smem4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();
-        for (int i = tid; i < HGC * kTQ * (D / 4); i += nthr) {
-            const int hh = i / (kTQ * (D / 4)), t = (i / (D / 4)) % kTQ, c4 = i % (D / 4);
-            const int n = rown[t];
-            const float4 v = n >= 0 ? ld_row4(p.X + ((size_t)n * h + h0 + hh) * D + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            *reinterpret_cast<float4 *>(Xs + (hh * kTQ + t) * XP + 4 * c4) = v;
-        }
         const int maxlen = soff[kTQ];
-        // ---- histograms of all heads of the group; per chunk the pairs [c0, c0 + kPR) of every row are staged as
-        // slice[row][kPRP] (128 B runs of one row -> coalesced loads; pitch 33 -> conflict-free reads by lanes = rows)
-        for (int c0 = 0; c0 < maxlen; c0 += kPR) {
-            if (c0 > 0) __syncthreads();   // previous chunk consumed
-            for (int i = tid; i < kTQ * kPR; i += nthr) {
-                const int t = i / kPR, j = i - t * kPR;
-                if (c0 + j >= soff[t]) continue;
-                const int gpos = gst[t] + c0 + j;
-                const int m = PERM && !(p.w_by_slot && p.packed) ? __ldg(p.pair_id + gpos) : gpos;
-                const int mw = p.w_by_slot ? gpos : m;
-                const int o = t * kPRP + j;
-                if (p.packed) {
-                    const unsigned q = __ldg(p.packed + gpos);   // 10-bit fields -> 8-bit fields
-                    pk[o] = (q & 0xffu) | (((q >> 10) & 0xffu) << 8) | (((q >> 20) & 0xffu) << 16);
-                } else {
-                    const unsigned r0 = clampi(__ldg(p.rel_idx + 3 * (size_t)m + 0), L - 1);
-                    const unsigned r1 = clampi(__ldg(p.rel_idx + 3 * (size_t)m + 1), L - 1);
-                    const unsigned r2 = clampi(__ldg(p.rel_idx + 3 * (size_t)m + 2), L - 1);
-                    pk[o] = r0 | (r1 << 8) | (r2 << 16);
-                }
+        // X rows of the tile: loads issued here, stored together with the first pair slice below
+        float4 xv[XE];
 #pragma unroll
-                for (int hh = 0; hh < HGC; ++hh) sw[hh * kPC + o] = __ldg(p.w + (size_t)mw * h + h0 + hh);
+        for (int e = 0; e < XE; ++e) {
+            const int i = tid + e * nthr;
+            xv[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < HGC * kTQ * (D / 4)) {
+                const int hh = i / (kTQ * (D / 4)), t = (i / (D / 4)) % kTQ, c4 = i % (D / 4);
+                const int n = rown[t];
+                if (n >= 0) xv[e] = ld_row4(p.X + ((size_t)n * h + h0 + hh) * D + 4 * c4);
+            }
+        }
+        // ---- histograms of all heads of the group; per chunk the pairs [c0, c0 + kPR) of every row are staged as
+        // slice[row][kPRP] (128 B runs of one row -> coalesced loads; pitch 33 -> conflict-free reads by lanes = rows).
+        // All global loads of a chunk are issued before the first shared-memory store (one memory round trip).
+        for (int c0 = 0; c0 < maxlen || c0 == 0; c0 += kPR) {
+            if (c0 > 0) __syncthreads();   // previous chunk consumed
+            unsigned sq[SE];
+            float swv[SE][HGC];
+            int so[SE];
+#pragma unroll
+            for (int e = 0; e < SE; ++e) {
+                const int i = tid + e * nthr;
+                const int t = i / kPR, j = i - t * kPR;
+                so[e] = -1;
+                if (i < kTQ * kPR && c0 + j < soff[t]) {
+                    const int gpos = gst[t] + c0 + j;
+                    const int m = PERM && !(p.w_by_slot && p.packed) ? __ldg(p.pair_id + gpos) : gpos;
+                    const int mw = p.w_by_slot ? gpos : m;
+                    so[e] = t * kPRP + j;
+                    if (p.packed) {
+                        sq[e] = __ldg(p.packed + gpos);
+                    } else {
+                        const unsigned r0 = clampi(__ldg(p.rel_idx + 3 * (size_t)m + 0), L - 1);
+                        const unsigned r1 = clampi(__ldg(p.rel_idx + 3 * (size_t)m + 1), L - 1);
+                        const unsigned r2 = clampi(__ldg(p.rel_idx + 3 * (size_t)m + 2), L - 1);
+                        sq[e] = r0 | (r1 << 10) | (r2 << 20);
+                    }
+#pragma unroll
+                    for (int hh = 0; hh < HGC; ++hh) swv[e][hh] = __ldg(p.w + (size_t)mw * h + h0 + hh);
+                }
+            }
+            if (c0 == 0) {
+#pragma unroll
+                for (int e = 0; e < XE; ++e) {
+                    const int i = tid + e * nthr;
+                    if (i < HGC * kTQ * (D / 4)) {
+                        const int hh = i / (kTQ * (D / 4)), t = (i / (D / 4)) % kTQ, c4 = i % (D / 4);
+                        *reinterpret_cast<float4 *>(Xs + (hh * kTQ + t) * XP + 4 * c4) = xv[e];
+                    }
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < SE; ++e) {
+                if (so[e] < 0) continue;
+                const unsigned q = sq[e];   // 10-bit fields -> 8-bit fields
+                pk[so[e]] = (q & 0xffu) | (((q >> 10) & 0xffu) << 8) | (((q >> 20) & 0xffu) << 16);
+#pragma unroll
+                for (int hh = 0; hh < HGC; ++hh) sw[hh * kPC + so[e]] = swv[e][hh];
             }
             __syncthreads();
             for (int item = tid; item < HGC * 3 * kTQ; item += nthr) {   // one thread per (head, axis, row)

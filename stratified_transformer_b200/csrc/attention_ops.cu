@@ -21,6 +21,7 @@
 //     a per-row histogram (3 scalar adds per pair-head instead of 3*d atomics) followed by a register-tiled
 //     fp32 outer-product accumulation; one flush of red.global.add per CTA at the end.
 #include <algorithm>
+#include <type_traits>
 #include <cstdlib>
 
 #include <cub/cub.cuh>
@@ -217,16 +218,17 @@ __global__ void __launch_bounds__(kMaxSegThreads) seg_reduce_kernel(const SegPar
                 const int j_l = HAS_Y ? ld_stream(p.gather_idx + tl) : 0;
                 unsigned pk_l = 0;
                 if (HAS_T) pk_l = p.packed ? __ldg(p.packed + tl) : pack_bins(p.rel_idx + 3 * (size_t)m_l, L);
-                constexpr int U = 2;   // pair slots per lane group in flight (U * HG row gathers)
-                for (int s0 = 0; s0 < cnt; s0 += NS * U) {
-                    float4 val[U][HG];
-                    float wv[U][HG];
-                    bool act[U];
+                // A step takes UU pair slots per lane group (UU * HG row gathers in flight).  Full steps use two slots;
+                // a tail of at most NS pairs takes a one-slot step, so a row wastes fewer than NS pair slots.
+                auto step = [&](auto uu_c, int s0) {
+                    constexpr int UU = decltype(uu_c)::value;
+                    float4 val[UU][HG];
+                    float wv[UU][HG];
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
+                    for (int u = 0; u < UU; ++u) {
                         const int pl = s0 + u * NS + slot;
-                        act[u] = pl < cnt;
-                        const int pc = act[u] ? pl : cnt - 1;
+                        const bool act = pl < cnt;
+                        const int pc = act ? pl : cnt - 1;
                         const int m = need_m ? __shfl_sync(0xffffffffu, m_l, pc) : c0 + pc;
                         const int mw = p.w_by_slot ? c0 + pc : m;
                         const int j = HAS_Y ? __shfl_sync(0xffffffffu, j_l, pc) : 0;
@@ -234,17 +236,20 @@ __global__ void __launch_bounds__(kMaxSegThreads) seg_reduce_kernel(const SegPar
                         const int r0 = pk & 0x3ff, r1 = (pk >> 10) & 0x3ff, r2 = pk >> 20;
 #pragma unroll
                         for (int hh = 0; hh < HG; ++hh) {
-                            wv[u][hh] = act[u] ? ld_stream(p.w + (size_t)mw * h + h0 + hh) : 0.f;
+                            wv[u][hh] = act ? ld_stream(p.w + (size_t)mw * h + h0 + hh) : 0.f;
                             val[u][hh] = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (HAS_Y) val[u][hh] = ld_row4(p.Y + (size_t)j * C + (h0 + hh) * D + 4 * g);
                             if (HAS_T) val[u][hh] = f4_add(table_sum4<D, HG, kReduceTableCopies<D>>(ts, L, r0, r1, r2, hh, gc), val[u][hh]);
                         }
                     }
 #pragma unroll
-                    for (int u = 0; u < U; ++u)
+                    for (int u = 0; u < UU; ++u)
 #pragma unroll
                         for (int hh = 0; hh < HG; ++hh) acc[hh] = f4_fma(wv[u][hh], val[u][hh], acc[hh]);
-                }
+                };
+                int s0 = 0;
+                for (; s0 + NS < cnt; s0 += 2 * NS) step(std::integral_constant<int, 2>{}, s0);
+                if (s0 < cnt) step(std::integral_constant<int, 1>{}, s0);
             }
 #pragma unroll
             for (int hh = 0; hh < HG; ++hh) {

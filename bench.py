@@ -46,8 +46,8 @@ HEAD_DIM = 16
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scenes", type=int, default=8)
     ap.add_argument("--points", type=int, default=80000)
@@ -364,11 +364,17 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    marks = []
     for _ in range(a.steps):
         one_step()
+        if os.environ.get("STB200_BENCH_STEP_TIMES"):   # development aid: per-step device times on stderr
+            marks.append(torch.cuda.Event(enable_timing=True)); marks[-1].record()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / a.steps
+    if marks and rank == 0:
+        ts = [e0.elapsed_time(marks[0])] + [marks[i - 1].elapsed_time(marks[i]) for i in range(1, len(marks))]
+        print("step ms:", " ".join(f"{t:.1f}" for t in ts), file=sys.stderr)
     _cabi.profile_enable(False)
     prof = _cabi.profile_dump()
     launches = (_cabi.launch_count() - launches0) // a.steps

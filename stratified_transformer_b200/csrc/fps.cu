@@ -407,12 +407,14 @@ extern "C" int stb200_furthestsampling(int b, int n, const float *xyz, const int
     const int logB = ref_block_log2(n);
     // cluster size: as many CTAs per scene as keep all scenes co-resident (148 SMs), but never more threads than points
     // tuning overrides (development): STB200_FPS_CLUSTER caps the cluster size, STB200_FPS_THREADS sets the CTA size
-    // large scenes: 128-thread CTAs (one warp per scheduler, 40 points per thread) measured faster than 256 x 20
-    const int threads = env_int("STB200_FPS_THREADS", n > 16 * kFpsThreads * 12 ? 128 : kFpsThreads);
+    const int threads = env_int("STB200_FPS_THREADS", kFpsThreads);
     // target points per thread when choosing the cluster size: small scenes spread over more CTAs (measured)
     const int per_thread = env_int("STB200_FPS_POINTS", n > 8192 ? 10 : 3);
     int cs = 1;
-    while (cs < env_int("STB200_FPS_CLUSTER", kMaxCluster) && b * cs * 2 <= kNumSMs && cs * threads * per_thread < n) cs <<= 1;
+    // All clusters together take at most half of the SMs: the kernel is latency-bound (one CTA per SM, few issue
+    // slots used) and normally runs beside the attention kernels of the previous batch (GeometryPrefetcher); 8 scenes
+    // x 8 CTAs x 256 threads cost 8 % more FPS time than 16 x 128 but 2.4 % less step time in that pipeline.
+    while (cs < env_int("STB200_FPS_CLUSTER", kMaxCluster) && b * cs * 2 <= kNumSMs / 2 && cs * threads * per_thread < n) cs <<= 1;
     for (; cs >= 1; cs >>= 1) {
         // A thread's points are i = gtid + u * (cs * threads); "first strict maximum inside the thread" equals the
         // reference's tie order only if they all share i mod B, i.e. cs * threads must be a multiple of B.

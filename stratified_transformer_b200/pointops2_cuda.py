@@ -222,6 +222,11 @@ def dot_prod_with_idx_backward_cuda_v2(N, M, h, hdim, n_max, T, grad_out, q, ind
 
 # ------------------------------------------------------------------------------------------------
 def furthestsampling_cuda(b, n, xyz, offset, new_offset, tmp, idx):
+    """same positional arguments as the reference pybind function (sampling/sampling_cuda_kernel.h:7).  `tmp` (the
+    reference's 1e10-filled scratch) is only read by the streaming fallback for scenes that do not fit the
+    register-resident cluster kernel; None allocates it here."""
+    if tmp is None:
+        tmp = torch.full((xyz.shape[0],), 1e10, dtype=torch.float32, device=xyz.device)
     _cabi.call("stb200_furthestsampling", int(b), int(n), _f(xyz, "xyz"), _i(offset, "offset"),
                _i(new_offset, "new_offset"), None if tmp is None else _f(tmp, "tmp"), _i(idx, "idx"), _stream())
 

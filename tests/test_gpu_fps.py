@@ -73,3 +73,15 @@ def test_fps_full_size_scene():
     want = fps_oracle.furthestsampling(xyz, offset, new_offset)
     got = ours(xyz, offset, new_offset)
     assert np.array_equal(got, want)
+
+
+def test_fps_streaming_fallback_for_very_large_scene():
+    """A 200k-point scene exceeds the register-resident cluster kernel (16 CTAs x 256 threads x 40 points): the
+    streaming kernel takes over (scratch allocated by the wrapper) and must give the same exact result."""
+    rng = np.random.default_rng(5)
+    n = 200_000
+    xyz = rng.uniform(0, 10, (n, 3)).astype(np.float32)
+    offset = np.array([n], np.int32)
+    new_offset = io.fps_new_offset(offset, 64)
+    want = fps_oracle.furthestsampling(xyz, offset, new_offset)
+    assert np.array_equal(ours(xyz, offset, new_offset), want)

@@ -81,7 +81,9 @@ def run_layer_fused(dev):
 
 
 @pytest.mark.parametrize("N,M,h,d,L", [(3500, 80000, 6, 16, 31), (700, 30000, 3, 16, 64), (500, 9000, 4, 32, 20),
-                                       (300, 6000, 24, 16, 80), (64, 40, 2, 16, 5)])
+                                       (300, 6000, 24, 16, 80), (64, 40, 2, 16, 5),
+                                       (400, 12000, 3, 16, 100),    # 3L = 300 table rows: two passes of the table-gradient kernel
+                                       (200, 5000, 2, 32, 180)])    # 540 rows: three passes, head dim 32
 def test_fused_entry_points_vs_oracle(N, M, h, d, L):
     cpu, dev = make_case(N, M, h, d, L, seed=3, dist="randn")
     got = run_layer_fused(dev)
@@ -103,6 +105,7 @@ def oracle_layer(cpu):
     (257, 4000, 5, 16, 7, "randn"),        # h with no divisor in {2,3,4}
     (300, 6000, 24, 16, 64, "randn"),      # S3DIS layer-3 head count
     (64, 40, 2, 16, 5, "rand"),            # mostly empty segments
+    (400, 12000, 3, 16, 100, "randn"),     # table longer than one table-gradient pass (3L > 256)
 ])
 def test_layer_fwd_bwd_vs_oracle(N, M, h, d, L, dist):
     cpu, dev = make_case(N, M, h, d, L, seed=1, dist=dist)

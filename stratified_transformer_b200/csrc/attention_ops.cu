@@ -32,7 +32,7 @@ namespace stb200 {
 
 constexpr int kThreads = 256;
 constexpr int kMaxSegThreads = 512;   // seg_dot / seg_reduce may run with 256 or 512 threads per CTA (same staged tables, more warps)
-constexpr int kRowsPerChunk = 64;  // rows (queries or keys) a CTA takes per grid-stride step
+constexpr int kRowsPerChunk = 64;  // rows (queries or keys) a CTA takes per grid-stride step (upper bound, see rows_per_chunk)
 
 struct SegParams {
     int N, h, L;
@@ -49,6 +49,7 @@ struct SegParams {
     float *out;
     int accumulate;
     int w_by_slot;          // PERM kernels: w is already in segment-slot (transposed) order, index it by slot instead of pair id
+    int rows_per_chunk;     // rows a CTA takes per grid-stride step: 64, fewer for small N so that every CTA gets >= 8 steps
 };
 
 // Copy one head group of a [L,h,D,3] table into shared memory as [axis][l][hh][copy][c].
@@ -125,8 +126,8 @@ __global__ void __launch_bounds__(kMaxSegThreads, (EX || EY) ? 2 : 1) seg_dot_ke
     const int grp = lane / G, g = lane % G;
     float4 *xw = reinterpret_cast<float4 *>(xs + warp * HG * D);
 
-    for (int base_n = blockIdx.x * kRowsPerChunk; base_n < p.N; base_n += gridDim.x * kRowsPerChunk) {
-        const int end_n = min(p.N, base_n + kRowsPerChunk);
+    for (int base_n = blockIdx.x * p.rows_per_chunk; base_n < p.N; base_n += gridDim.x * p.rows_per_chunk) {
+        const int end_n = min(p.N, base_n + p.rows_per_chunk);
         for (int nn = base_n + warp; nn < end_n; nn += nwarps) {
             const int n = p.row_order ? __ldg(p.row_order + nn) : nn;
             const int start = __ldg(p.offsets + n), len = __ldg(p.offsets + n + 1) - start;
@@ -202,8 +203,8 @@ __global__ void __launch_bounds__(kMaxSegThreads) seg_reduce_kernel(const SegPar
     const int slot = lane / G, g = lane % G;
     const int gc = (kReduceTableCopies<D> == 2 ? (slot & 1) * G : 0) + g;
 
-    for (int base_n = blockIdx.x * kRowsPerChunk; base_n < p.N; base_n += gridDim.x * kRowsPerChunk) {
-        const int end_n = min(p.N, base_n + kRowsPerChunk);
+    for (int base_n = blockIdx.x * p.rows_per_chunk; base_n < p.N; base_n += gridDim.x * p.rows_per_chunk) {
+        const int end_n = min(p.N, base_n + p.rows_per_chunk);
         for (int nn = base_n + warp; nn < end_n; nn += nwarps) {
             const int n = p.row_order ? __ldg(p.row_order + nn) : nn;
             const int start = __ldg(p.offsets + n), end = __ldg(p.offsets + n + 1);
@@ -804,10 +805,17 @@ static int seg_waves() {
     return max(1, env);
 }
 
-static int grid_rows(int N, size_t smem, int groups) {
-    const int chunks = (N + kRowsPerChunk - 1) / kRowsPerChunk;
+// Grid and row-chunk size of a segment kernel.  A CTA walks chunks of consecutive rows (window-sorted rows share their
+// gathered k/v rows in L1); with few rows (deep layers) 64-row chunks would leave CTAs with 3 vs 4 chunks, i.e. a 25 %
+// tail, so the chunk shrinks (down to 16 rows) until every CTA has at least 8 of them.
+static int grid_rows(int N, size_t smem, int groups, int *rows_per_chunk) {
     const int ctas_per_sm = (int)max((size_t)1, min((size_t)4, (size_t)(220 * 1024) / max(smem, (size_t)1)));
-    return max(1, min(chunks, (kNumSMs * ctas_per_sm * seg_waves() + groups - 1) / groups));
+    const int ctas = max(1, (kNumSMs * ctas_per_sm * seg_waves() + groups - 1) / groups);
+    static const int env_rpc = getenv("STB200_SEG_ROWS_PER_CHUNK") ? atoi(getenv("STB200_SEG_ROWS_PER_CHUNK")) : 0;
+    int rpc = env_rpc > 0 ? env_rpc : max(16, min(kRowsPerChunk, N / (ctas * 8)));
+    *rows_per_chunk = rpc;
+    const int chunks = (N + rpc - 1) / rpc;
+    return max(1, min(chunks, ctas));
 }
 
 template <typename K>
@@ -855,10 +863,11 @@ static int launch_seg_dot_hg(const SegParams &p, int M, const char *name, cudaSt
     const size_t smem = ((size_t)(EX + EY) * 3 * p.L * HG * D + (threads / kWarp) * HG * D) * sizeof(float);
     auto kern = seg_dot_kernel<D, HG, XY, EX, EY>;
     if (int rc = prep_smem(kern, smem)) return rc;
-    dim3 grid(grid_rows(p.N, smem, p.h / HG), p.h / HG);
+    SegParams pl = p;
+    dim3 grid(grid_rows(p.N, smem, p.h / HG, &pl.rows_per_chunk), p.h / HG);
     {
         KernelScope ks(name, seg_bytes(p, D, M, true, true, false, true, false, EX + EY, true), s);
-        kern<<<grid, threads, smem, s>>>(p);
+        kern<<<grid, threads, smem, s>>>(pl);
     }
     return check_launch(name);
 }
@@ -885,10 +894,11 @@ static int launch_seg_reduce_hg(const SegParams &p, int M, const char *name, cud
     const size_t smem = (size_t)HAS_T * 3 * p.L * HG * D * kReduceTableCopies<D> * sizeof(float);
     auto kern = seg_reduce_kernel<D, HG, HAS_Y, HAS_T, PERM>;
     if (int rc = prep_smem(kern, smem)) return rc;
-    dim3 grid(grid_rows(p.N, smem, p.h / HG), p.h / HG);
+    SegParams pl = p;
+    dim3 grid(grid_rows(p.N, smem, p.h / HG, &pl.rows_per_chunk), p.h / HG);
     {
         KernelScope ks(name, seg_bytes(p, D, M, false, HAS_Y, true, HAS_Y, PERM, HAS_T, false), s);
-        kern<<<grid, seg_threads(HAS_T && !PERM, true), smem, s>>>(p);
+        kern<<<grid, seg_threads(HAS_T && !PERM, true), smem, s>>>(pl);
     }
     return check_launch(name);
 }

@@ -51,3 +51,25 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     import pytest
     with pytest.raises(_cabi.Stb200Error, match="no CPU fallback"):
         _cabi.load()
+
+
+def test_index_struct_mirror_matches_the_header(tmp_path):
+    """ctypes mirror of `stb200_index` == the C struct in include/stb200.h (size and every field offset), checked by
+    compiling a tiny C program against the header with the host compiler."""
+    import shutil
+    import subprocess
+    import pytest
+    from stratified_transformer_b200 import _cabi
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no host C compiler")
+    fields = [name for name, _ in _cabi.IndexStruct._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "stb200.h"\nint main(void) {\n'
+                   '  printf("%zu\\n", sizeof(stb200_index));\n' +
+                   "".join(f'  printf("%zu\\n", offsetof(stb200_index, {f}));\n' for f in fields) + "  return 0;\n}\n")
+    exe = tmp_path / "layout"
+    subprocess.run([cc, "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert out[0] == ctypes.sizeof(_cabi.IndexStruct)
+    assert out[1:] == [getattr(_cabi.IndexStruct, f).offset for f in fields]

@@ -1,16 +1,15 @@
 #!/bin/bash
-# Sweep table-gradient launch knobs (heads per CTA, waves) and print per-kernel ms per step, solo and overlapped.
-for cfg in "3 1" "2 1" "1 1" "1 2" "2 2"; do
-  set -- $cfg
-  export STB200_TG_HEADS=$1 STB200_TG_WAVES=$2
-  for mode in "--no-overlap" ""; do
-  echo "== tg_heads=$1 tg_waves=$2 $mode"
-  python bench.py --no-e2e --no-cpu-baseline --steps 8 --warmup 3 $mode | python -c "
+# Development aid: A/B the launch knobs of the hot kernels on the bench step (overlapped, device-resident).
+#   tools/sweep_seg.sh "STB200_TG_WAVES=2" "STB200_SEGRED_THREADS=512" ...
+# Each argument is a space-separated list of VAR=value settings for one run; a baseline run comes first and last.
+run() {
+  env $1 python bench.py --no-e2e --no-cpu-baseline --steps 12 --warmup 3 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-print('ms_per_step', round(d['ms_per_step'],2))
 k=d['roofline']['per_kernel_ms_per_step']
-print({a:b for a,b in k.items() if a.startswith('table')})
+print('%-40s %7.2f ms/step   ' % ('$1' or 'baseline', d['ms_per_step']), {a: round(b, 2) for a, b in k.items() if a.startswith(('seg_', 'table'))})
 "
-  done
-done
+}
+run ""
+for cfg in "$@"; do run "$cfg"; done
+run ""

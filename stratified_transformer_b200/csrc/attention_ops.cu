@@ -77,6 +77,22 @@ __device__ __forceinline__ void stage_table(float *dst, const float *__restrict_
     }
 }
 
+// seg_dot with a three-head group: four 64 B slots per (axis, bin) = [h0, h1, h2, h2] (256 B, slot parity = bank half).
+// The two lane groups of an LDS.128 quarter-warp hold consecutive items (pair, head): (h0,h1) and (h1,h2) of one pair
+// sit in different halves by construction; the pair-crossing case (h2 of one pair, h0 of the next) takes the second
+// copy of h2 in the other half - so no look-up ever has a bank conflict (ncu before: 15 % of the shared wavefronts).
+template <int D>
+__device__ __forceinline__ void stage_table_3in4(float *dst, const float *__restrict__ src, int L, int h, int h0) {
+    const int total = 3 * L * 4 * D;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int c = i % D;
+        const int slot = (i / D) % 4;
+        const int l = (i / (D * 4)) % L;
+        const int a = i / (D * 4 * L);
+        dst[i] = __ldg(src + ((size_t)(l * h + h0 + min(slot, 2)) * D + c) * 3 + a);
+    }
+}
+
 __device__ __forceinline__ int clampi(int v, int hi) { return min(max(v, 0), hi); }
 
 constexpr int kUnroll = 4;  // independent row gathers kept in flight per lane
@@ -107,24 +123,31 @@ __device__ __forceinline__ float4 table_sum4(const float *ts, int L, int r0, int
 // A warp owns a query; its len*HG (pair, head) items are spread over 32/G lane groups of G=D/4 lanes.
 // Table variants run 512 threads per CTA; capping them at 64 registers keeps two CTAs (32 warps) resident per SM,
 // which hides the shared-memory look-up latency better than the 80-register / 16-warp build (measured: -20 %).
-template <int D, int HG, bool XY, bool EX, bool EY>
+template <int D, int HG, bool XY, bool EX, bool EY, bool PAD = false>
 __global__ void __launch_bounds__(kMaxSegThreads, (EX || EY) ? 2 : 1) seg_dot_kernel(const SegParams p) {
     extern __shared__ float4 smem4[];
     float *smem = reinterpret_cast<float *>(smem4);
     constexpr int G = D / 4, NS = kWarp / G;
+    constexpr int RS = PAD ? 4 : HG;   // 64 B slots per (axis, bin): PAD = three heads in four slots, see stage_table_3in4
+    static_assert(!PAD || (HG == 3 && D == 16), "the padded layout is for three 16-float heads");
     const int L = p.L, h = p.h, C = p.h * D;
     const int h0 = blockIdx.y * HG;
-    const int tsz = 3 * L * HG * D;
+    const int tsz = 3 * L * RS * D;
     float *tx = smem;
     float *ty = tx + (EX ? tsz : 0);
     float *xs = ty + (EY ? tsz : 0);
-    if (EX) stage_table<D, HG, 1>(tx, p.Tx, L, h, h0);
-    if (EY) stage_table<D, HG, 1>(ty, p.Ty, L, h, h0);
+    if (PAD) {
+        if (EX) stage_table_3in4<D>(tx, p.Tx, L, h, h0);
+        if (EY) stage_table_3in4<D>(ty, p.Ty, L, h, h0);
+    } else {
+        if (EX) stage_table<D, HG, 1>(tx, p.Tx, L, h, h0);
+        if (EY) stage_table<D, HG, 1>(ty, p.Ty, L, h, h0);
+    }
     if (EX || EY) __syncthreads();
 
     const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp, nwarps = blockDim.x / kWarp;
     const int grp = lane / G, g = lane % G;
-    float4 *xw = reinterpret_cast<float4 *>(xs + warp * HG * D);
+    float4 *xw = reinterpret_cast<float4 *>(xs + warp * RS * D);
 
     for (int base_n = blockIdx.x * p.rows_per_chunk; base_n < p.N; base_n += gridDim.x * p.rows_per_chunk) {
         const int end_n = min(p.N, base_n + p.rows_per_chunk);
@@ -133,7 +156,7 @@ __global__ void __launch_bounds__(kMaxSegThreads, (EX || EY) ? 2 : 1) seg_dot_ke
             const int start = __ldg(p.offsets + n), len = __ldg(p.offsets + n + 1) - start;
             if (len <= 0) continue;
             __syncwarp();
-            for (int i = lane; i < HG * G; i += kWarp) xw[i] = ld_row4(p.X + (size_t)n * C + h0 * D + 4 * i);
+            for (int i = lane; i < RS * G; i += kWarp) xw[i] = ld_row4(p.X + (size_t)n * C + (h0 + min(i / G, HG - 1)) * D + 4 * (i % G));
             __syncwarp();
             // 32 pairs at a time: one coalesced load of the key ids (and the packed rel-pos bins) per chunk,
             // handed to the lane groups with shuffles; kUnroll independent row gathers in flight per lane.
@@ -161,14 +184,17 @@ __global__ void __launch_bounds__(kMaxSegThreads, (EX || EY) ? 2 : 1) seg_dot_ke
 #pragma unroll
                     for (int u = 0; u < kUnroll; ++u) {
                         if (e0 + u * NS >= items) break;   // warp-uniform
-                        const float4 x4 = xw[hh[u] * G + g];
+                        // PAD: head 2 has a copy in either bank half; an even lane group takes the upper one (its
+                        // quarter-warp partner then holds head 0 of the next pair), an odd one the lower (partner: head 1)
+                        const int sl = PAD && hh[u] == 2 ? 3 - (grp & 1) : hh[u];
+                        const float4 x4 = xw[sl * G + g];
                         float acc = 0.f;
                         if (XY) acc = f4_dot(x4, y4[u], acc);
                         if (EX || EY) {
                             const unsigned pk = __shfl_sync(0xffffffffu, pk_l, pl[u]);
                             const int r0 = pk & 0x3ff, r1 = (pk >> 10) & 0x3ff, r2 = pk >> 20;
-                            if (EX) acc = f4_dot(x4, table_sum4<D, HG, 1>(tx, L, r0, r1, r2, hh[u], g), acc);
-                            if (EY) acc = f4_dot(y4[u], table_sum4<D, HG, 1>(ty, L, r0, r1, r2, hh[u], g), acc);
+                            if (EX) acc = f4_dot(x4, table_sum4<D, RS, 1>(tx, L, r0, r1, r2, sl, g), acc);
+                            if (EY) acc = f4_dot(y4[u], table_sum4<D, RS, 1>(ty, L, r0, r1, r2, sl, g), acc);
                         }
                         acc = group_sum<G>(acc);
                         if (act[u] && g == 0) p.out[(size_t)(start + c0 + pl[u]) * h + h0 + hh[u]] = acc;
@@ -860,8 +886,16 @@ static double seg_bytes(const SegParams &p, int D, int M, bool rows_x, bool rows
 template <int D, int HG, bool XY, bool EX, bool EY>
 static int launch_seg_dot_hg(const SegParams &p, int M, const char *name, cudaStream_t s) {
     const int threads = seg_threads(EX + EY);
-    const size_t smem = ((size_t)(EX + EY) * 3 * p.L * HG * D + (threads / kWarp) * HG * D) * sizeof(float);
-    auto kern = seg_dot_kernel<D, HG, XY, EX, EY>;
+    // three-head groups: conflict-free padded table layout when two CTAs with it still fit an SM
+    static const bool pad_env = !(getenv("STB200_SEGDOT_NOPAD") && atoi(getenv("STB200_SEGDOT_NOPAD")));
+    constexpr bool kCanPad = HG == 3 && D == 16 && (EX || EY);
+    const size_t smem_pad = ((size_t)(EX + EY) * 3 * p.L * 4 * D + (threads / kWarp) * 4 * D) * sizeof(float);
+    const bool pad = kCanPad && pad_env && 2 * (smem_pad + 1024) <= 227 * 1024;
+    const size_t smem = pad ? smem_pad : ((size_t)(EX + EY) * 3 * p.L * HG * D + (threads / kWarp) * HG * D) * sizeof(float);
+    void (*kern)(const SegParams) = seg_dot_kernel<D, HG, XY, EX, EY, false>;
+    if constexpr (kCanPad) {
+        if (pad) kern = seg_dot_kernel<D, HG, XY, EX, EY, true>;
+    }
     if (int rc = prep_smem(kern, smem)) return rc;
     SegParams pl = p;
     dim3 grid(grid_rows(p.N, smem, p.h / HG, &pl.rows_per_chunk), p.h / HG);

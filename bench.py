@@ -54,7 +54,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="build the geometry serially inside the step instead of prefetching it on a side stream")
-    ap.add_argument("--fused", action="store_true", help="use the experimental fused per-window forward kernel in the device arm")
+    ap.add_argument("--fused", action="store_true", help="(round-1 experiment) per-window mma.sync forward kernel in the per-op device arm")
+    ap.add_argument("--path", default="fused", choices=["fused", "perop"],
+                    help="fused: window-centric fused kernels on the work plan (default); perop: the per-pair entry points on the CSR pair list")
     ap.add_argument("--no-profile", action="store_true", help="do not bracket kernels with CUDA events in the timed region")
     ap.add_argument("--cpu-sample-points", type=int, default=0, help="points of the CPU sample scene (0 = auto)")
     return ap.parse_args()
@@ -270,13 +272,45 @@ def device_step(levels, grads_out, geo=None, no_fused=True):
     return grads_out
 
 
+def device_step_fused(levels, grads_out, geo):
+    """One pass of the hot path on the window-centric fused kernels: per block one forward (dense pass + sparse pass) that
+    keeps only the output and the row log-sum-exp, and one backward producing the six gradients.  No [M,h] tensor."""
+    from stratified_transformer_b200 import _cabi
+    stream = torch.cuda.current_stream().cuda_stream
+    for lvl, lv in enumerate(levels):
+        cfg = lv["cfg"]
+        h, L = cfg["h"], lv["L"]
+        li = geo[lvl]
+        q, k, v, g = lv["q"], lv["k"], lv["v"], lv["g"]
+        N = q.shape[0]
+        dev = q.device
+        for blk in range(cfg["depth"]):
+            plan = li.for_block(blk).plan
+            passes, n_passes = plan.passes(L)
+            tq, tk, tv = lv["tables"][blk]
+            out = torch.empty(N, h, HEAD_DIM, device=dev)
+            lse = torch.empty(N, h, device=dev); lsum = torch.empty(N, h, device=dev)
+            _cabi.call("stb200_fused_attention_forward", passes, n_passes, N, h, L, q.data_ptr(), k.data_ptr(), v.data_ptr(),
+                       tq.data_ptr(), tk.data_ptr(), tv.data_ptr(), out.data_ptr(), lse.data_ptr(), lsum.data_ptr(), stream)
+            gq = torch.empty_like(q)
+            alloc = torch.zeros_like if plan.needs_zeroed_key_grads else torch.empty_like
+            gk, gv = alloc(k), alloc(v)
+            gtq, gtk, gtv = torch.zeros_like(tq), torch.zeros_like(tk), torch.zeros_like(tv)
+            _cabi.call("stb200_fused_attention_backward", passes, n_passes, N, h, L, g.data_ptr(), out.data_ptr(), lse.data_ptr(),
+                       q.data_ptr(), k.data_ptr(), v.data_ptr(), tq.data_ptr(), tk.data_ptr(), tv.data_ptr(), gq.data_ptr(),
+                       gk.data_ptr(), gv.data_ptr(), gtq.data_ptr(), gtk.data_ptr(), gtv.data_ptr(), stream)
+            grads_out.append((gtq, gtk, gtv))
+    return grads_out
+
+
 class HotPathModel(torch.nn.Module):
     """e2e harness: the package's WindowAttention modules in the S3DIS schedule.  The blocks outside the hot path are
     replaced by stand-ins that keep shapes right (a Linear stem 6 -> 48, and `Linear(C_l -> C_{l+1})` on the points the
     precomputed hierarchy keeps instead of TransitionDown); residual connection around each attention block."""
 
-    def __init__(self):
+    def __init__(self, fused=True):
         super().__init__()
+        self.fused = fused
         from stratified_transformer_b200.window_attention import WindowAttention
         self.stem = torch.nn.Linear(6, LAYERS[0]["C"])
         self.down = torch.nn.ModuleList([torch.nn.Linear(LAYERS[i]["C"], LAYERS[i + 1]["C"]) for i in range(len(LAYERS) - 1)])
@@ -290,7 +324,8 @@ class HotPathModel(torch.nn.Module):
         for lvl, cfg in enumerate(LAYERS):
             if lvl > 0:
                 feats = self.down[lvl - 1](feats[sub_idx[lvl].long()])
-            li = geo[lvl] if geo is not None else index.build_layer_index(xyzs[lvl], offsets[lvl], cfg["window"], cfg["quant"], DS_SCALE)
+            li = geo[lvl] if geo is not None else index.build_layer_index(xyzs[lvl], offsets[lvl], cfg["window"], cfg["quant"], DS_SCALE,
+                                                                          fused=self.fused, csr=not self.fused)
             for blk, attn in enumerate(self.blocks[lvl]):
                 feats = feats + attn(feats, xyzs[lvl], li.for_block(blk))
         return feats.float().pow(2).mean()
@@ -333,10 +368,11 @@ def main():
     offs_d = [lv["offset"] for lv in levels]
     offs_h = [lv["offset"].cpu().tolist() for lv in levels]
     pf = None
+    use_fused = a.path == "fused"
     if not a.no_overlap:
         # geometry (FPS + pair lists) of the NEXT batch runs on a side stream under the attention of the current one;
         # every step still computes one complete geometry from the coordinates
-        pf = st_index.GeometryPrefetcher(geo_cfgs, dev)
+        pf = st_index.GeometryPrefetcher(geo_cfgs, dev, fused=use_fused, csr=not use_fused)
         pf.submit(xyzs_d, offs_d, offs_h)
 
     def one_step():
@@ -344,7 +380,13 @@ def main():
         if pf is not None:
             geo = pf.take()
             pf.submit(xyzs_d, offs_d, offs_h)
-        grads = device_step(levels, [], geo, not a.fused)
+        if use_fused:
+            if geo is None:
+                geo = [st_index.build_layer_index(lv["xyz"], lv["offset"], lv["cfg"]["window"], lv["cfg"]["quant"], DS_SCALE,
+                                                  fused=True, csr=False) for lv in levels]
+            grads = device_step_fused(levels, [], geo)
+        else:
+            grads = device_step(levels, [], geo, not a.fused)
         if pf is not None:
             pf.complete()
         if dist is not None:   # training only: data-parallel gradient all-reduce of the attention parameters
@@ -389,7 +431,7 @@ def main():
     e2e = None
     if not a.no_e2e:
         torch.manual_seed(0)
-        model = HotPathModel().to(dev)
+        model = HotPathModel(use_fused).to(dev)
         if dist is not None:
             model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])
         host = dict(feat6=torch.cat([rgb, levels[0]["xyz"].cpu()], 1).pin_memory(),
@@ -400,7 +442,7 @@ def main():
             sum(s.numel() * 4 for s in host["sub"] if s is not None)
 
         main = torch.cuda.current_stream()
-        pf2 = None if a.no_overlap else st_index.GeometryPrefetcher(geo_cfgs, dev)
+        pf2 = None if a.no_overlap else st_index.GeometryPrefetcher(geo_cfgs, dev, fused=use_fused, csr=not use_fused)
 
         def upload(stream):
             with torch.cuda.stream(stream):

@@ -43,7 +43,8 @@ extern "C" {
 const char *stb200_last_error(void);
 /* number of kernels this library launched since load (bench.py's "gpu_launches") */
 long long stb200_launch_count(void);
-/* ABI version: 100 = first release, 101 = stb200_index has len_order / t_len_order (append-only struct growth) */
+/* ABI version: 100 = first release, 101 = stb200_index has len_order / t_len_order (append-only struct growth),
+ * 102 = fused work plan + fused window attention entry points */
 int stb200_version(void);
 /* Optional per-kernel profiler: when enabled every launch is bracketed by CUDA events on its stream.
  * stb200_profile_dump writes a JSON object {"kernel name": {"launches", "ms", "bytes"}} (bytes = algorithmic bytes
@@ -255,6 +256,62 @@ int stb200_window_attention_forward_fused(const stb200_index *ix, int n_win, con
 /* segment softmax restricted to a list of rows (rows = NULL: all N rows) */
 int stb200_segment_softmax_forward_rows(int n_rows, const int *rows, int h, const float *a, const float *b,
                                         const int *index0_offsets, float *p, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Window-centric fused attention (no reference counterpart as an op): the whole pair path of
+ * WindowAttention.forward (model/stratified_transformer.py:183-210: attention_step1_v2 + dot_prod_with_idx_v3 + add +
+ * scatter_softmax + attention_step2_with_rel_pos_value_v2) and its backward, without any [M,h] tensor.  It consumes a
+ * WORK PLAN instead of the CSR pair list: the same pairs (get_indice_pairs, :10-42) expressed as
+ *   dense tiles  : per small window the [n x n] matrix of packed rel-pos bins (r0 | r1<<8 | r2<<16), queries x keys;
+ *   sparse tiles : per large window [n_V x n_s] (queries = its points, keys = its FPS-sampled points), bit 31 set where
+ *                  the reference drops the pair (equal window_coord, :28-35);
+ *   items        : blocks of at most BQ x BK of those matrices (struct of 8 ints: q_pos, nq, k_pos, nk, rel_off,
+ *                  rel_pitch, flags, pad), grouped by key-chunk ordinal; one pass (= one launch) per ordinal.
+ * Build it right after stb200_stratified_pairs_count on the same builder workspace (the CSR arrays are not needed):
+ *   stb200_fused_plan_count -> totals[40] (device; ints): [0] dense rel words, [1] sparse rel words, [2] large windows,
+ *       [3] largest small window, [4] most sampled keys of a large window, [5] error bits (1/2: a window needs more than 8
+ *       key chunks, 4: more than 2^31 rel words), [6],[7] min / max dense bin (after fill), [8..15] dense items per ordinal,
+ *       [16..23] sparse items per ordinal;   the caller reads it, allocates, then calls
+ *   stb200_fused_plan_fill.  swin != 0: rel-pos index of model/swin3d_transformer.py:151-154 (dense only).
+ * Dense blocks are square (BQ == BK).  Kernels are built for blocks 64x64, 48x32 and 32x32; head dim 16. */
+typedef struct stb200_fused_pass {
+    const void *items;       /* device, n_items x 8 ints, all of one ordinal */
+    int n_items;
+    const int *q_order;      /* sorted position -> point id of the query rows (dense: by small window; sparse: by large window) */
+    const int *k_order;      /* ... of the key rows (dense: same array; sparse: sampled points grouped by large window) */
+    const unsigned *rel;     /* tiles */
+    const int *pos_win;      /* dense only (NULL marks a sparse pass): small-window rank of a sorted position [N] */
+    const int *wstart;       /* dense only: window boundaries [n_win+1] */
+    const int *tile_base;    /* dense only: first rel word of every window's tile [n_win] */
+    int bin_lo, RB;          /* bins [bin_lo, bin_lo+RB) of every axis are staged (products are only computed for those) */
+    int BQ, BK;
+} stb200_fused_pass;
+
+size_t stb200_fused_plan_scratch_bytes(int N);
+int stb200_fused_plan_count(int N, void *builder_workspace, size_t builder_workspace_bytes, int has_sparse, int BQ, int BK, int BQS,
+                            int BKS, void *scratch, size_t scratch_bytes, int *totals, void *stream);
+int stb200_fused_plan_fill(int N, const float *xyz, float window_size_x2, float quant_size, int has_sparse, int BQ, int BK, int BQS,
+                           int BKS, int swin, float swin_window, float swin_shift, void *builder_workspace,
+                           size_t builder_workspace_bytes, void *scratch, size_t scratch_bytes, int *totals, unsigned *dense_rel,
+                           int *tile_base, int *pos_win, int *order_s, int *wstart_s, void *dense_items, unsigned *sparse_rel,
+                           int *order_l, int *samp, int n_samp, void *sparse_items, void *stream);
+/* Forward: passes in launch order (dense ordinals, then sparse ordinals).  out [N,h,16]; m, l [N,h] scratch: after the call m
+ * holds the log-sum-exp of every (query, head) row, which the backward pass takes as `lse`.  Nothing needs zero-filling. */
+int stb200_fused_attention_forward(const stb200_fused_pass *passes, int n_passes, int N, int h, int L, const float *q, const float *k,
+                                   const float *v, const float *table_q, const float *table_k, const float *table_v, float *out,
+                                   float *m, float *l, void *stream);
+/* Backward: grad_q is overwritten; grad_k / grad_v are overwritten by the dense pass except for windows larger than BK, whose
+ * key rows are accumulated into (zero-fill grad_k / grad_v when totals[3] > BK); table gradients are accumulated into. */
+int stb200_fused_attention_backward(const stb200_fused_pass *passes, int n_passes, int N, int h, int L, const float *grad_out,
+                                    const float *out, const float *lse, const float *q, const float *k, const float *v,
+                                    const float *table_q, const float *table_k, const float *table_v, float *grad_q, float *grad_k,
+                                    float *grad_v, float *grad_table_q, float *grad_table_k, float *grad_table_v, void *stream);
+
+/* Self-test of the tcgen05 building blocks the fused kernels use (csrc/tc_umma.cuh): one CTA computes a 3xTF32 GEMM through
+ * tensor memory.  mode 0: A [M,K], B [N,K] -> A B^T (both K-major); mode 1: A [K,M], B [K,N] -> A^T B (both MN-major);
+ * mode 2: A [M,K] (K-major), B [K,N] (MN-major) -> A B.  M in {64, 128}, N, K multiples of 8.  out [128, N] receives TMEM
+ * lanes 0..127 of the accumulator; *status becomes 1 when the MMA never signalled completion. */
+int stb200_tc_selftest(int mode, int M, int N, int K, const float *A, const float *B, float *out, int *status, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * k nearest neighbours per scene — replaces knnquery_cuda_launcher

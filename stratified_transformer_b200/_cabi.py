@@ -25,6 +25,16 @@ class IndexStruct(ctypes.Structure):
 
 _IX = ctypes.POINTER(IndexStruct)
 
+
+class FusedPass(ctypes.Structure):
+    """mirror of `stb200_fused_pass` (include/stb200.h)"""
+    _fields_ = [("items", ctypes.c_void_p), ("n_items", ctypes.c_int), ("q_order", ctypes.c_void_p), ("k_order", ctypes.c_void_p),
+                ("rel", ctypes.c_void_p), ("pos_win", ctypes.c_void_p), ("wstart", ctypes.c_void_p), ("tile_base", ctypes.c_void_p),
+                ("bin_lo", ctypes.c_int), ("RB", ctypes.c_int), ("BQ", ctypes.c_int), ("BK", ctypes.c_int)]
+
+
+_FP = ctypes.POINTER(FusedPass)
+
 # name -> argtypes (every function returns int unless listed in _RESTYPES)
 _SIGNATURES = {
     "stb200_transpose_csr": [_c_int, _c_int, P, P, P, P, P, P, _c_size_t, P],
@@ -61,6 +71,12 @@ _SIGNATURES = {
     "stb200_classify_windows": [_c_int, P, P, P, P, P, P, P, P],
     "stb200_window_attention_forward_fused": [_IX, _c_int, P, P, _c_int, _c_int, _c_int] + [P] * 9,
     "stb200_segment_softmax_forward_rows": [_c_int, P, _c_int, P, P, P, P, P],
+    "stb200_fused_plan_count": [_c_int, P, _c_size_t, _c_int, _c_int, _c_int, _c_int, _c_int, P, _c_size_t, P, P],
+    "stb200_fused_plan_fill": [_c_int, P, ctypes.c_float, ctypes.c_float] + [_c_int] * 6 + [ctypes.c_float, ctypes.c_float, P, _c_size_t,
+                               P, _c_size_t] + [P] * 10 + [_c_int, P, P],
+    "stb200_fused_attention_forward": [_FP, _c_int, _c_int, _c_int, _c_int] + [P] * 10,
+    "stb200_fused_attention_backward": [_FP, _c_int, _c_int, _c_int, _c_int] + [P] * 16,
+    "stb200_tc_selftest": [_c_int] * 4 + [P] * 5,
     "stb200_rel_pos_index_swin": [_c_int, P, P, P, ctypes.c_float, ctypes.c_float, ctypes.c_float, _c_int, P, P, P, P],
 }
 _RESTYPES = {
@@ -72,6 +88,7 @@ _RESTYPES = {
     "stb200_window_logits_backward_workspace_bytes": (_c_size_t, [_c_int, _c_int]),
     "stb200_pair_builder_workspace_bytes": (_c_size_t, [_c_int]),
     "stb200_fused_max_keys": (_c_int, []),
+    "stb200_fused_plan_scratch_bytes": (_c_size_t, [_c_int]),
     "stb200_profile_enable": (None, [_c_int]),
     "stb200_profile_dump": (_c_size_t, [ctypes.c_char_p, _c_size_t]),
 }
@@ -103,8 +120,8 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = restype
-    if lib.stb200_version() < 101:   # the IndexStruct mirror below needs the 101 layout (len_order / t_len_order)
-        raise Stb200Error(f"{LIB_PATH} is stale (ABI {lib.stb200_version()} < 101): rebuild it with `make -C stratified_transformer_b200/csrc`")
+    if lib.stb200_version() < 102:   # the IndexStruct mirror below needs the 101 layout (len_order / t_len_order)
+        raise Stb200Error(f"{LIB_PATH} is stale (ABI {lib.stb200_version()} < 102): rebuild it with `make -C stratified_transformer_b200/csrc`")
     _lib = lib
     return lib
 

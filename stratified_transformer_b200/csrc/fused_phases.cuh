@@ -28,6 +28,7 @@
 
 #if defined(__CUDACC__) && !defined(FW_HOST_EMU)
 #define FW_FN __device__ __forceinline__
+#define FW_HD __host__ __device__ inline
 #define FW_PHASE_BEGIN {
 #define FW_PHASE_END } __syncthreads();
 #define FW_TID ((int)threadIdx.x)
@@ -37,6 +38,7 @@
 #else
 #include <vector_types.h>
 #define FW_FN inline
+#define FW_HD inline
 #define FW_PHASE_BEGIN for (int fw_tid_ = 0; fw_tid_ < NT; ++fw_tid_) {
 #define FW_PHASE_END }
 #define FW_TID fw_tid_
@@ -86,11 +88,11 @@ struct Layout {   // offsets in floats into the CTA's shared memory
     int tq, tk, tv, qT, kT, gT, vT, vR, QT, KT, GT, S, GS, U, rowinfo, keyid, red, mrow, lrow, drow, total;
 };
 
-FW_FN int fw_max(int a, int b) { return a > b ? a : b; }
-FW_FN int fw_min(int a, int b) { return a < b ? a : b; }
-FW_FN int round4(int x) { return (x + 3) & ~3; }
+FW_HD int fw_max(int a, int b) { return a > b ? a : b; }
+FW_HD int fw_min(int a, int b) { return a < b ? a : b; }
+FW_HD int round4(int x) { return (x + 3) & ~3; }
 
-inline Layout make_layout(int BQ, int BK, int Rpad, bool bwd) {
+FW_HD Layout make_layout(int BQ, int BK, int Rpad, bool bwd) {
     Layout y;
     y.Rpad = Rpad;
     y.RP = Rpad + 4;                 // product row pitch: multiple of 4 (vector stores), = 4 mod 8

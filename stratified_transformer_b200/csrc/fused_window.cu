@@ -1,0 +1,107 @@
+// Fused window attention, forward and backward: kernels around the CTA bodies of fused_phases.cuh and their C ABI.
+//
+// Replaces the pair path of WindowAttention.forward (/root/reference/model/stratified_transformer.py:183-210) and its
+// backward for pair lists that come from the device builder (pair_builder.cu): one launch per pass
+// (dense windows, key chunk 0, 1, ...; then sparse keys per large window, key chunk 0, 1, ...).  Persistent CTAs, each bound
+// to one head (its three table slices stay in shared memory) and striding over the pass's work items.
+#include "common.cuh"
+#include "fused_phases.cuh"
+
+namespace stb200 {
+
+using fw::PassParams;
+
+template <int BQ, int BK, bool BWD>
+__global__ void __launch_bounds__(fw::NT, 1) fused_window_kernel(const PassParams P, int ctas_per_head) {
+    extern __shared__ __align__(16) float fw_smem[];
+    const int head = blockIdx.x / ctas_per_head, cta = blockIdx.x - head * ctas_per_head;
+    if (BWD) fw::backward_cta<BQ, BK>(P, head, cta, ctas_per_head, fw_smem);
+    else fw::forward_cta<BQ, BK>(P, head, cta, ctas_per_head, fw_smem);
+}
+
+constexpr size_t kMaxSmem = 232448;   // 227 KB opt-in limit per CTA on sm_100a
+
+template <int BQ, int BK, bool BWD>
+static int launch_pass(const PassParams &P, const char *name, double bytes, cudaStream_t s) {
+    const fw::Layout y = fw::make_layout(BQ, BK, P.Rpad, BWD);
+    const size_t smem = (size_t)y.total * sizeof(float);
+    STB200_REQUIRE(smem <= kMaxSmem, STB200_ERR_ARG, "fused window attention: %zu B of shared memory needed for blocks %dx%d with %d staged bins",
+                   smem, BQ, BK, P.RB);
+    static bool attr_set = false;   // per instantiation
+    if (!attr_set) {
+        const cudaError_t e = cudaFuncSetAttribute(fused_window_kernel<BQ, BK, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+        STB200_REQUIRE(e == cudaSuccess, STB200_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    // one CTA per SM; CTAs of a head are consecutive
+    int per_head = kNumSMs / P.h;
+    if (per_head < 1) per_head = 1;
+    if (per_head > P.n_items) per_head = P.n_items;
+    KernelScope ks(name, bytes, s);
+    fused_window_kernel<BQ, BK, BWD><<<per_head * P.h, fw::NT, smem, s>>>(P, per_head);
+    return STB200_OK;
+}
+
+template <bool BWD>
+static int dispatch_pass(const stb200_fused_pass &ps, PassParams &P, const char *name, double bytes, cudaStream_t s) {
+    P.items = (const fw::Item *)ps.items;
+    P.n_items = ps.n_items;
+    P.q_order = ps.q_order; P.k_order = ps.k_order; P.rel = ps.rel;
+    P.pos_win = ps.pos_win; P.wstart = ps.wstart; P.tile_base = ps.tile_base;
+    P.bin_lo = ps.bin_lo; P.RB = ps.RB;
+    P.Rpad = (3 * ps.RB + 7) / 8 * 8;
+    STB200_REQUIRE(ps.RB > 0 && P.Rpad <= 256, STB200_ERR_ARG, "fused window attention stages at most 85 bins per axis (got %d)", ps.RB);
+    if (ps.BQ == 64 && ps.BK == 64) return launch_pass<64, 64, BWD>(P, name, bytes, s);
+    if (ps.BQ == 48 && ps.BK == 32) return launch_pass<48, 32, BWD>(P, name, bytes, s);
+    if (ps.BQ == 32 && ps.BK == 32) return launch_pass<32, 32, BWD>(P, name, bytes, s);
+    set_error("fused window attention: no kernel for blocks %dx%d (built: 64x64, 48x32, 32x32)", ps.BQ, ps.BK);
+    return STB200_ERR_ARG;
+}
+
+}  // namespace stb200
+
+using namespace stb200;
+
+extern "C" {
+
+int stb200_fused_attention_forward(const stb200_fused_pass *passes, int n_passes, int N, int h, int L, const float *q, const float *k,
+                                   const float *v, const float *table_q, const float *table_k, const float *table_v, float *out,
+                                   float *m, float *l, void *stream) {
+    STB200_REQUIRE(passes && n_passes > 0 && N > 0 && h > 0 && L > 0, STB200_ERR_ARG, "bad sizes");
+    STB200_REQUIRE(q && k && v && table_q && table_k && table_v && out && m && l, STB200_ERR_ARG, "null pointer");
+    PassParams P{};
+    P.L = L; P.h = h;
+    P.q = q; P.k = k; P.v = v; P.tq = table_q; P.tk = table_k; P.tv = table_v;
+    P.out = out; P.m = m; P.l = l;
+    for (int i = 0; i < n_passes; ++i) {
+        if (passes[i].n_items <= 0) continue;
+        // fused accounting: q, k, v read + out written once per point, spread over the passes by their share of rows
+        const double bytes = 4.0 * N * h * 16 * 4 / n_passes;
+        const int rc = dispatch_pass<false>(passes[i], P, passes[i].pos_win ? "fused_fwd[dense]" : "fused_fwd[sparse]", bytes, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return check_launch("fused_attention_forward");
+}
+
+int stb200_fused_attention_backward(const stb200_fused_pass *passes, int n_passes, int N, int h, int L, const float *grad_out,
+                                    const float *out, const float *lse, const float *q, const float *k, const float *v,
+                                    const float *table_q, const float *table_k, const float *table_v, float *grad_q, float *grad_k,
+                                    float *grad_v, float *grad_table_q, float *grad_table_k, float *grad_table_v, void *stream) {
+    STB200_REQUIRE(passes && n_passes > 0 && N > 0 && h > 0 && L > 0, STB200_ERR_ARG, "bad sizes");
+    STB200_REQUIRE(grad_out && out && lse && q && k && v && table_q && table_k && table_v && grad_q && grad_k && grad_v && grad_table_q &&
+                       grad_table_k && grad_table_v, STB200_ERR_ARG, "null pointer");
+    PassParams P{};
+    P.L = L; P.h = h;
+    P.q = q; P.k = k; P.v = v; P.tq = table_q; P.tk = table_k; P.tv = table_v;
+    P.out = const_cast<float *>(out); P.g = grad_out; P.lse = lse;
+    P.gq = grad_q; P.gk = grad_k; P.gv = grad_v; P.gtq = grad_table_q; P.gtk = grad_table_k; P.gtv = grad_table_v;
+    for (int i = 0; i < n_passes; ++i) {
+        if (passes[i].n_items <= 0) continue;
+        const double bytes = 4.0 * N * h * 16 * 8 / n_passes;
+        const int rc = dispatch_pass<true>(passes[i], P, passes[i].pos_win ? "fused_bwd[dense]" : "fused_bwd[sparse]", bytes, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return check_launch("fused_attention_backward");
+}
+
+}  // extern "C"

@@ -372,6 +372,246 @@ __global__ void swin_rel_kernel(int N, const float *__restrict__ xq, const int *
     }
 }
 
+
+// ---- work plan of the fused window-attention kernels (fused_window.cu; spec: oracle/fused_plan_oracle.py) -----------
+// Dense tiles: per small window the [n x n] matrix of packed rel-pos bins; sparse tiles: per large window the
+// [n_V x n_s] matrix (queries = its points, keys = its sampled points) with bit 31 set where get_indice_pairs drops the
+// pair (equal window_coord, model/stratified_transformer.py:28-35).  Items = blocks of <= BQ x BK of those matrices.
+constexpr int kPlanSeg = 128;     // small windows per greedy-packing segment
+constexpr int kPlanMaxOrd = 8;    // key chunks per window the launch sequence supports
+enum { PT_MDENSE = 0, PT_STOT = 1, PT_NWIN_L = 2, PT_MAXWIN = 3, PT_MAXNS = 4, PT_ERR = 5, PT_BINMIN = 6, PT_BINMAX = 7,
+       PT_DENSE_ITEMS = 8, PT_SPARSE_ITEMS = 16, PT_CURSOR_D = 24, PT_CURSOR_S = 32, PT_INTS = 40 };
+
+struct PlanItem { int q_pos, nq, k_pos, nk, rel_off, rel_pitch, flags, pad; };   // == stb200::fw::Item
+enum { PF_PACKED = 1, PF_FIRST = 2, PF_FINAL = 4, PF_KEY_ATOMIC = 8 };
+
+struct PlanScratch {
+    long long *sq, *sv;      // [N+1] tile sizes (n^2 per small window, n_V*n_s per large window) -> exclusive scans
+    long long *tb, *sb;      // tile bases
+    float *xq;               // [N,3] Swin per-point quantised coordinates
+    void *cub_tmp;           // scan temp storage (64-bit sums: more than the builder's int scans need for small N)
+    size_t cub_bytes;
+};
+static size_t plan_carve(PlanScratch &ps, char *base, int N) {
+    size_t o = 0;
+    auto take = [&](size_t bytes) { char *p = base ? base + o : nullptr; o += al(bytes); return p; };
+    const size_t nl = (size_t)(N + 1) * sizeof(long long);
+    ps.sq = (long long *)take(nl); ps.sv = (long long *)take(nl); ps.tb = (long long *)take(nl); ps.sb = (long long *)take(nl);
+    ps.xq = (float *)take((size_t)N * 3 * sizeof(float));
+    ps.cub_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, ps.cub_bytes, (const long long *)nullptr, (long long *)nullptr, N + 1);
+    ps.cub_tmp = take(ps.cub_bytes);
+    return o + 256;
+}
+
+// walks the small windows of one segment the way oracle/fused_plan_oracle.py does; EMIT = false only counts
+template <bool EMIT>
+__device__ void plan_dense_segment(int seg, int n_win, const int *__restrict__ wstart, const long long *__restrict__ tb, int BQ,
+                                   int BK, int final_flag, int *totals, const int *__restrict__ ord_off, PlanItem *items) {
+    const int w0 = seg * kPlanSeg, w1 = min(w0 + kPlanSeg, n_win);
+    int cur_start = -1, cur_rows = 0, n_packed = 0, max_win = 0;
+    auto flush = [&]() {
+        if (cur_rows) {
+            if (EMIT) {
+                const int slot = ord_off[0] + atomicAdd(&totals[PT_CURSOR_D], 1);
+                items[slot] = PlanItem{cur_start, cur_rows, cur_start, cur_rows, 0, 0, PF_PACKED | PF_FIRST | final_flag, 0};
+            }
+            ++n_packed;
+        }
+        cur_start = -1;
+        cur_rows = 0;
+    };
+    for (int w = w0; w < w1; ++w) {
+        const int ws = wstart[w], n = wstart[w + 1] - ws;
+        max_win = max(max_win, n);
+        if (n > BK) {
+            flush();
+            const int nc = (n + BK - 1) / BK;
+            if (nc > kPlanMaxOrd) { if (!EMIT) atomicOr(&totals[PT_ERR], 1); continue; }
+            for (int kc = 0; kc < nc; ++kc) {
+                if (!EMIT) { atomicAdd(&totals[PT_DENSE_ITEMS + kc], nc); continue; }
+                for (int qc = 0; qc < nc; ++qc) {
+                    const int qa = qc * BQ, ka = kc * BK;
+                    const int slot = ord_off[kc] + atomicAdd(&totals[PT_CURSOR_D + kc], 1);
+                    items[slot] = PlanItem{ws + qa, min(BQ, n - qa), ws + ka, min(BK, n - ka), (int)(tb[w] + (long long)qa * n + ka), n,
+                                           (kc == 0 ? PF_FIRST : 0) | PF_KEY_ATOMIC | (kc == nc - 1 ? final_flag : 0), 0};
+                }
+            }
+            continue;
+        }
+        if (cur_rows + n > BQ) flush();
+        if (cur_rows == 0) cur_start = ws;
+        cur_rows += n;
+    }
+    flush();
+    if (!EMIT) {
+        if (n_packed) atomicAdd(&totals[PT_DENSE_ITEMS], n_packed);
+        atomicMax(&totals[PT_MAXWIN], max_win);
+    }
+}
+
+__global__ void plan_count_kernel(int N, const int *__restrict__ rank_s, const int *__restrict__ rank_l,
+                                  const int *__restrict__ wstart_s, const int *__restrict__ wstart_l, const int *__restrict__ spos,
+                                  int has_sparse, int BQ, int BK, int BQS, int BKS, long long *sq, long long *sv, int *totals) {
+    const int n_win = rank_s[N - 1], n_win_l = rank_l[N - 1];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    for (int w = t; w <= N; w += nt) {
+        long long a = 0, b = 0;
+        if (w < n_win) { const long long n = wstart_s[w + 1] - wstart_s[w]; a = n * n; }
+        if (has_sparse && w < n_win_l) {
+            const long long nv = wstart_l[w + 1] - wstart_l[w], ns = spos[wstart_l[w + 1]] - spos[wstart_l[w]];
+            b = nv * ns;
+            const int nkc = max(1, (int)((ns + BKS - 1) / BKS)), nqc = (int)((nv + BQS - 1) / BQS);
+            if (nkc > kPlanMaxOrd) atomicOr(&totals[PT_ERR], 2);
+            else for (int kc = 0; kc < nkc; ++kc) atomicAdd(&totals[PT_SPARSE_ITEMS + kc], nqc);
+            atomicMax(&totals[PT_MAXNS], (int)ns);
+        }
+        sq[w] = a;
+        sv[w] = b;
+    }
+    const int n_seg = (n_win + kPlanSeg - 1) / kPlanSeg;
+    for (int seg = t; seg < n_seg; seg += nt) plan_dense_segment<false>(seg, n_win, wstart_s, nullptr, BQ, BK, 0, totals, nullptr, nullptr);
+    if (t == 0) totals[PT_NWIN_L] = has_sparse ? n_win_l : 0;
+}
+
+__global__ void plan_totals_kernel(int N, const long long *__restrict__ tb, const long long *__restrict__ sb, int *totals) {
+    if (threadIdx.x || blockIdx.x) return;
+    if (tb[N] >= (1LL << 31) || sb[N] >= (1LL << 31)) totals[PT_ERR] |= 4;
+    totals[PT_MDENSE] = (int)tb[N];
+    totals[PT_STOT] = (int)sb[N];
+}
+
+__global__ void plan_items_kernel(int N, const int *__restrict__ rank_s, const int *__restrict__ rank_l,
+                                  const int *__restrict__ wstart_s, const int *__restrict__ wstart_l, const int *__restrict__ spos,
+                                  int has_sparse, int BQ, int BK, int BQS, int BKS, const long long *__restrict__ tb,
+                                  const long long *__restrict__ sb, int *totals, PlanItem *dense_items, PlanItem *sparse_items) {
+    __shared__ int ord_d[kPlanMaxOrd], ord_s[kPlanMaxOrd];
+    if (threadIdx.x == 0) {
+        int a = 0, b = 0;
+        for (int o = 0; o < kPlanMaxOrd; ++o) {
+            ord_d[o] = a; a += totals[PT_DENSE_ITEMS + o];
+            ord_s[o] = b; b += totals[PT_SPARSE_ITEMS + o];
+        }
+    }
+    __syncthreads();
+    const int n_win = rank_s[N - 1], n_win_l = rank_l[N - 1];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    const int n_seg = (n_win + kPlanSeg - 1) / kPlanSeg;
+    for (int seg = t; seg < n_seg; seg += nt)
+        plan_dense_segment<true>(seg, n_win, wstart_s, tb, BQ, BK, has_sparse ? 0 : PF_FINAL, totals, ord_d, dense_items);
+    if (has_sparse)
+        for (int v = t; v < n_win_l; v += nt) {
+            const int vs = wstart_l[v], nv = wstart_l[v + 1] - vs;
+            const int ss = spos[vs], ns = spos[wstart_l[v + 1]] - ss;
+            const int nkc = max(1, (ns + BKS - 1) / BKS), nqc = (nv + BQS - 1) / BQS;
+            if (nkc > kPlanMaxOrd) continue;
+            for (int kc = 0; kc < nkc; ++kc)
+                for (int qc = 0; qc < nqc; ++qc) {
+                    const int qa = qc * BQS, ka = kc * BKS;
+                    const int slot = ord_s[kc] + atomicAdd(&totals[PT_CURSOR_S + kc], 1);
+                    sparse_items[slot] = PlanItem{vs + qa, min(BQS, nv - qa), ss + ka, max(0, min(BKS, ns - ka)),
+                                                  (int)(sb[v] + (long long)qa * ns + ka), ns, PF_KEY_ATOMIC | (kc == nkc - 1 ? PF_FINAL : 0), 0};
+                }
+        }
+}
+
+__device__ __forceinline__ unsigned pack_bins(int r0, int r1, int r2, int *bmin, int *bmax) {
+    *bmin = min(*bmin, min(r0, min(r1, r2)));
+    *bmax = max(*bmax, max(r0, max(r1, r2)));
+    return (unsigned)(r0 & 0xff) | ((unsigned)(r1 & 0xff) << 8) | ((unsigned)(r2 & 0xff) << 16);
+}
+
+// one warp per sorted position: the row of its window's dense tile (and of its large window's sparse tile)
+__global__ void plan_tiles_kernel(int N, const float *__restrict__ xyz, const int *__restrict__ order_s, const int *__restrict__ rank_s,
+                                  const int *__restrict__ wstart_s, const long long *__restrict__ tb, const int *__restrict__ order_l,
+                                  const int *__restrict__ rank_l, const int *__restrict__ wstart_l, const int *__restrict__ spos,
+                                  const int *__restrict__ samp, const int4 *__restrict__ wc, const long long *__restrict__ sb,
+                                  int has_sparse, int swin, const float *__restrict__ xq, float swin_bias, float two_w, float quant,
+                                  unsigned *__restrict__ drel, unsigned *__restrict__ srel, int *__restrict__ pos_win, int *totals) {
+    const int lane = threadIdx.x % kWarp;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) / kWarp, nw = gridDim.x * blockDim.x / kWarp;
+    int bmin = 1 << 30, bmax = -(1 << 30);
+    for (int p = wid; p < N; p += nw) {
+        {   // dense row
+            const int a = order_s[p], w = rank_s[p] - 1;
+            const int ws = wstart_s[w], n = wstart_s[w + 1] - ws;
+            if (lane == 0) pos_win[p] = w;
+            unsigned *row = drel + tb[w] + (long long)(p - ws) * n;
+            if (swin) {
+                const float xa = xq[(size_t)a * 3], ya = xq[(size_t)a * 3 + 1], za = xq[(size_t)a * 3 + 2];
+                for (int t = lane; t < n; t += kWarp) {
+                    const int b = order_s[ws + t];
+                    row[t] = pack_bins((int)__fadd_rn(__fsub_rn(xa, xq[(size_t)b * 3]), swin_bias),
+                                       (int)__fadd_rn(__fsub_rn(ya, xq[(size_t)b * 3 + 1]), swin_bias),
+                                       (int)__fadd_rn(__fsub_rn(za, xq[(size_t)b * 3 + 2]), swin_bias), &bmin, &bmax);
+                }
+            } else {
+                const float xa = __ldg(xyz + (size_t)a * 3), ya = __ldg(xyz + (size_t)a * 3 + 1), za = __ldg(xyz + (size_t)a * 3 + 2);
+                for (int t = lane; t < n; t += kWarp) {
+                    const int b = order_s[ws + t];
+                    row[t] = pack_bins(rel_index_stratified(xa, __ldg(xyz + (size_t)b * 3), two_w, quant),
+                                       rel_index_stratified(ya, __ldg(xyz + (size_t)b * 3 + 1), two_w, quant),
+                                       rel_index_stratified(za, __ldg(xyz + (size_t)b * 3 + 2), two_w, quant), &bmin, &bmax);
+                }
+            }
+        }
+        if (has_sparse) {
+            const int a = order_l[p], v = rank_l[p] - 1;
+            const int vs = wstart_l[v];
+            const int s0 = spos[vs], ns = spos[wstart_l[v + 1]] - s0;
+            if (ns > 0) {
+                const float xa = __ldg(xyz + (size_t)a * 3), ya = __ldg(xyz + (size_t)a * 3 + 1), za = __ldg(xyz + (size_t)a * 3 + 2);
+                const int4 ca = wc[a];
+                unsigned *row = srel + sb[v] + (long long)(p - vs) * ns;
+                int d0 = 0, d1 = 0;   // the sparse pass stages the whole bin range: its extrema are not tracked
+                for (int t = lane; t < ns; t += kWarp) {
+                    const int b = samp[s0 + t];
+                    unsigned wd = pack_bins(rel_index_stratified(xa, __ldg(xyz + (size_t)b * 3), two_w, quant),
+                                            rel_index_stratified(ya, __ldg(xyz + (size_t)b * 3 + 1), two_w, quant),
+                                            rel_index_stratified(za, __ldg(xyz + (size_t)b * 3 + 2), two_w, quant), &d0, &d1);
+                    if (!wc_differs(ca, wc[b])) wd |= 0x80000000u;
+                    row[t] = wd;
+                }
+            }
+        }
+    }
+    bmin = __reduce_min_sync(0xffffffffu, bmin);
+    bmax = __reduce_max_sync(0xffffffffu, bmax);
+    if (lane == 0 && bmin <= bmax) {
+        atomicMin(&totals[PT_BINMIN], bmin);
+        atomicMax(&totals[PT_BINMAX], bmax);
+    }
+}
+
+__global__ void plan_init_totals_kernel(int *totals) {
+    const int i = threadIdx.x;
+    if (i < PT_INTS) totals[i] = i == PT_BINMIN ? (1 << 30) : (i == PT_BINMAX ? -(1 << 30) : 0);
+}
+
+__global__ void swin_quant_gp_kernel(int N, const float *__restrict__ xyz, const GridParams *__restrict__ gp, float shift, float w,
+                                     float quant, float *__restrict__ xq) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N * 3; i += gridDim.x * blockDim.x) {
+        const float t = __fadd_rn(__fsub_rn(__ldg(xyz + i), gp->mn[i % 3]), shift);
+        xq[i] = floor_div_f32(remainder_f32(t, w), quant);
+    }
+}
+
+
+__global__ void plan_export_kernel(int N, const int *__restrict__ rank_s, const long long *__restrict__ tb, const int *__restrict__ order_s,
+                                   const int *__restrict__ wstart_s, const int *__restrict__ order_l, const int *__restrict__ samp,
+                                   int n_samp, int has_sparse, int *tile_base, int *o_order_s, int *o_wstart_s, int *o_order_l, int *o_samp) {
+    const int n_win = rank_s[N - 1];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= N; i += gridDim.x * blockDim.x) {
+        if (i < n_win) tile_base[i] = (int)tb[i];
+        if (i <= n_win) o_wstart_s[i] = wstart_s[i];
+        if (i < N) {
+            o_order_s[i] = order_s[i];
+            if (has_sparse) o_order_l[i] = order_l[i];
+        }
+        if (has_sparse && i < n_samp) o_samp[i] = samp[i];
+    }
+}
+
 static int blocks_for(long long n, int per_block = 256, int cap = kNumSMs * 8) {
     return (int)max(1LL, min((n + per_block - 1) / per_block, (long long)cap));
 }
@@ -479,6 +719,74 @@ int stb200_rel_pos_index_swin(int N, const float *xyz, const int *index0_offsets
     swin_rel_kernel<<<blocks_for((long long)N * kWarp), 256, 0, s>>>(N, xq_scratch, index0_offsets, index_1,
                                                                     (float)(quant_grid_length - 1), rel_idx);
     return check_launch("rel_pos_index_swin");
+}
+
+
+// ---- fused work plan (include/stb200.h) ------------------------------------------------------------------------------
+size_t stb200_fused_plan_scratch_bytes(int N) {
+    PlanScratch ps;
+    return plan_carve(ps, nullptr, N < 1 ? 1 : N);
+}
+
+int stb200_fused_plan_count(int N, void *workspace, size_t workspace_bytes, int has_sparse, int BQ, int BK, int BQS, int BKS,
+                            void *scratch, size_t scratch_bytes, int *totals, void *stream) {
+    STB200_REQUIRE(N > 0 && workspace && scratch && totals, STB200_ERR_ARG, "null pointer / bad N");
+    STB200_REQUIRE(BQ == BK && BQ > 0 && BQS > 0 && BKS > 0, STB200_ERR_ARG, "dense blocks are square (BQ == BK)");
+    STB200_REQUIRE(workspace_bytes >= stb200_pair_builder_workspace_bytes(N), STB200_ERR_WORKSPACE, "builder workspace too small");
+    STB200_REQUIRE(scratch_bytes >= stb200_fused_plan_scratch_bytes(N), STB200_ERR_WORKSPACE, "plan scratch too small");
+    cudaStream_t s = (cudaStream_t)stream;
+    BuilderState st;
+    carve(st, (char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255), N);
+    PlanScratch ps;
+    plan_carve(ps, (char *)(((uintptr_t)scratch + 255) & ~(uintptr_t)255), N);
+    KernelScope ks("fused_plan_count[5 launches]", 0.0, s);
+    count_launch(4);
+    plan_init_totals_kernel<<<1, 64, 0, s>>>(totals);
+    plan_count_kernel<<<blocks_for(N + 1), 256, 0, s>>>(N, st.rank_s, st.rank_l, st.wstart_s, st.wstart_l, st.spos, has_sparse ? 1 : 0,
+                                                        BQ, BK, BQS, BKS, ps.sq, ps.sv, totals);
+    size_t tb = ps.cub_bytes;
+    cudaError_t e = cub::DeviceScan::ExclusiveSum(ps.cub_tmp, tb, ps.sq, ps.tb, N + 1, s);
+    STB200_REQUIRE(e == cudaSuccess, STB200_ERR_CUDA, "cub scan: %s", cudaGetErrorString(e));
+    tb = ps.cub_bytes;
+    e = cub::DeviceScan::ExclusiveSum(ps.cub_tmp, tb, ps.sv, ps.sb, N + 1, s);
+    STB200_REQUIRE(e == cudaSuccess, STB200_ERR_CUDA, "cub scan: %s", cudaGetErrorString(e));
+    plan_totals_kernel<<<1, 32, 0, s>>>(N, ps.tb, ps.sb, totals);
+    return check_launch("fused_plan_count");
+}
+
+int stb200_fused_plan_fill(int N, const float *xyz, float window_size_x2, float quant_size, int has_sparse, int BQ, int BK, int BQS,
+                           int BKS, int swin, float swin_window, float swin_shift, void *workspace, size_t workspace_bytes,
+                           void *scratch, size_t scratch_bytes, int *totals, unsigned *dense_rel, int *tile_base, int *pos_win,
+                           int *order_s, int *wstart_s, void *dense_items, unsigned *sparse_rel, int *order_l, int *samp, int n_samp,
+                           void *sparse_items, void *stream) {
+    STB200_REQUIRE(N > 0 && xyz && workspace && scratch && totals && dense_rel && tile_base && pos_win && order_s && wstart_s && dense_items,
+                   STB200_ERR_ARG, "null pointer / bad N");
+    STB200_REQUIRE(!has_sparse || (sparse_rel && order_l && samp && sparse_items), STB200_ERR_ARG, "sparse outputs missing");
+    STB200_REQUIRE(workspace_bytes >= stb200_pair_builder_workspace_bytes(N) && scratch_bytes >= stb200_fused_plan_scratch_bytes(N),
+                   STB200_ERR_WORKSPACE, "workspace too small");
+    cudaStream_t s = (cudaStream_t)stream;
+    BuilderState st;
+    carve(st, (char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255), N);
+    PlanScratch ps;
+    plan_carve(ps, (char *)(((uintptr_t)scratch + 255) & ~(uintptr_t)255), N);
+    KernelScope ks("fused_plan_fill[4 launches]", 0.0, s);
+    count_launch(3);
+    if (swin) {
+        const int qgl = (int)(swin_window / quant_size);
+        swin_quant_gp_kernel<<<blocks_for((long long)N * 3), 256, 0, s>>>(N, xyz, st.gp, swin_shift, swin_window, quant_size, ps.xq);
+        (void)qgl;
+    }
+    plan_items_kernel<<<blocks_for(N), 256, 0, s>>>(N, st.rank_s, st.rank_l, st.wstart_s, st.wstart_l, st.spos, has_sparse ? 1 : 0, BQ, BK,
+                                                    BQS, BKS, ps.tb, ps.sb, totals, (PlanItem *)dense_items, (PlanItem *)sparse_items);
+    const float swin_bias = swin ? (float)((int)(swin_window / quant_size) - 1) : 0.f;
+    plan_tiles_kernel<<<blocks_for((long long)N * kWarp), 256, 0, s>>>(N, xyz, st.order_s, st.rank_s, st.wstart_s, ps.tb, st.order_l,
+                                                                      st.rank_l, st.wstart_l, st.spos, st.samp, st.wc, ps.sb,
+                                                                      has_sparse ? 1 : 0, swin ? 1 : 0, ps.xq, swin_bias, window_size_x2,
+                                                                      quant_size, dense_rel, sparse_rel, pos_win, totals);
+    // tile bases as int32 (checked < 2^31 by plan_totals_kernel) + the sorted orders the kernels index with
+    plan_export_kernel<<<blocks_for(N + 1), 256, 0, s>>>(N, st.rank_s, ps.tb, st.order_s, st.wstart_s, st.order_l, st.samp, n_samp,
+                                                         has_sparse ? 1 : 0, tile_base, order_s, wstart_s, order_l, samp);
+    return check_launch("fused_plan_fill");
 }
 
 }  // extern "C"

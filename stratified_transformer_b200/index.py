@@ -23,6 +23,122 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+FUSED_BLOCKS = dict(BQ=64, BK=64, BQS=48, BKS=32)   # block shapes the fused kernels are built for (dense square, sparse 48x32)
+_PLAN_MAXORD = 8
+
+
+@dataclass
+class FusedPlan:
+    """Work plan of the window-centric fused kernels (include/stb200.h, "Window-centric fused attention"): the pair structure of
+    one block parity as dense tiles per small window + sparse tiles per large window + block items.  Built by the device
+    builder from the same window partition as the CSR pair list; replaces it on the fused path."""
+    N: int
+    totals: list                         # host copy of the 40 plan totals
+    dense_items: torch.Tensor            # [n,8] int32, grouped by key-chunk ordinal
+    dense_rel: torch.Tensor
+    tile_base: torch.Tensor
+    pos_win: torch.Tensor
+    order_s: torch.Tensor
+    wstart_s: torch.Tensor
+    sparse_items: torch.Tensor | None
+    sparse_rel: torch.Tensor | None
+    order_l: torch.Tensor | None
+    samp: torch.Tensor | None
+    blocks: dict
+    swin: bool = False
+    _passes: dict = field(default_factory=dict, repr=False)
+
+    @property
+    def max_window(self) -> int:
+        return self.totals[3]
+
+    @property
+    def needs_zeroed_key_grads(self) -> bool:
+        """windows larger than a block accumulate their key-side gradients from several items"""
+        return self.totals[3] > self.blocks["BK"]
+
+    def tensors(self):
+        return [t for t in (self.dense_items, self.dense_rel, self.tile_base, self.pos_win, self.order_s, self.wstart_s,
+                            self.sparse_items, self.sparse_rel, self.order_l, self.samp) if t is not None]
+
+    def bin_range(self, L: int, dense: bool):
+        """bins [lo, lo+RB) staged by a pass.  Dense pairs share a small window, |delta| < w: their bins lie in the middle
+        half of the table (model/stratified_transformer.py:186-188 with |r| < window_size); two bins of margin each side."""
+        if self.swin or not dense:
+            return 0, L
+        return max(L // 4 - 2, 0), (L + 1) // 2 + 4
+
+    def passes(self, L: int):
+        """(ctypes array of stb200_fused_pass in launch order, count) for table length L"""
+        ent = self._passes.get(L)
+        if ent is None:
+            lst = []
+            lo, RB = self.bin_range(L, True)
+            off = 0
+            for o in range(_PLAN_MAXORD):
+                n = self.totals[8 + o]
+                if n:
+                    lst.append(_cabi.FusedPass(self.dense_items.data_ptr() + off * 32, n, self.order_s.data_ptr(), self.order_s.data_ptr(),
+                                               self.dense_rel.data_ptr(), self.pos_win.data_ptr(), self.wstart_s.data_ptr(),
+                                               self.tile_base.data_ptr(), lo, RB, self.blocks["BQ"], self.blocks["BK"]))
+                off += n
+            if self.sparse_items is not None:
+                lo, RB = self.bin_range(L, False)
+                off = 0
+                for o in range(_PLAN_MAXORD):
+                    n = self.totals[16 + o]
+                    if n:
+                        lst.append(_cabi.FusedPass(self.sparse_items.data_ptr() + off * 32, n, self.order_l.data_ptr(), self.samp.data_ptr(),
+                                                   self.sparse_rel.data_ptr(), None, None, None, lo, RB, self.blocks["BQS"], self.blocks["BKS"]))
+                    off += n
+            ent = ((_cabi.FusedPass * len(lst))(*lst), len(lst))
+            self._passes[L] = ent
+        return ent
+
+
+def _plan_count(N, has_sparse, ws, blocks):
+    """enqueue the plan's counting pass on the builder workspace of a finished stb200_stratified_pairs_count"""
+    lib = _cabi.load()
+    nbytes = lib.stb200_fused_plan_scratch_bytes(N)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=ws.device)
+    totals = torch.empty(40, dtype=torch.int32, device=ws.device)
+    _cabi.call("stb200_fused_plan_count", N, ws.data_ptr(), ws.numel(), int(has_sparse), blocks["BQ"], blocks["BK"], blocks["BQS"],
+               blocks["BKS"], scratch.data_ptr(), nbytes, totals.data_ptr(), _stream())
+    return scratch, totals
+
+
+def _plan_fill(N, xyz, window_size, quant_size, n_win, n_samp, ws, scratch, totals_dev, totals, blocks, swin_shift=None) -> FusedPlan:
+    if totals[5]:
+        raise _cabi.Stb200Error(f"fused plan: unsupported window structure (error bits {totals[5]}: a window needs more than "
+                                f"{_PLAN_MAXORD} key chunks, or more than 2^31 tile words)")
+    dev = xyz.device
+    has_sparse = n_samp > 0
+
+    def i32(n):
+        return torch.empty(max(int(n), 1), dtype=torch.int32, device=dev)
+    n_dense_items = sum(totals[8:16])
+    n_sparse_items = sum(totals[16:24])
+    dense_items = torch.empty(max(n_dense_items, 1), 8, dtype=torch.int32, device=dev)
+    dense_rel, tile_base, pos_win, order_s, wstart_s = i32(totals[0]), i32(n_win), i32(N), i32(N), i32(n_win + 1)
+    sparse_items = sparse_rel = order_l = samp = None
+    if has_sparse:
+        sparse_items = torch.empty(max(n_sparse_items, 1), 8, dtype=torch.int32, device=dev)
+        sparse_rel, order_l, samp = i32(totals[1]), i32(N), i32(n_samp)
+    swin = swin_shift is not None
+    _cabi.call("stb200_fused_plan_fill", N, xyz.data_ptr(), float(2 * window_size), float(quant_size if quant_size is not None else 1.0),
+               int(has_sparse), blocks["BQ"], blocks["BK"], blocks["BQS"], blocks["BKS"], int(swin), float(window_size),
+               float(swin_shift or 0.0), ws.data_ptr(), ws.numel(), scratch.data_ptr(), scratch.numel(), totals_dev.data_ptr(),
+               dense_rel.data_ptr(), tile_base.data_ptr(), pos_win.data_ptr(), order_s.data_ptr(), wstart_s.data_ptr(),
+               dense_items.data_ptr(), None if sparse_rel is None else sparse_rel.data_ptr(),
+               None if order_l is None else order_l.data_ptr(), None if samp is None else samp.data_ptr(), int(n_samp),
+               None if sparse_items is None else sparse_items.data_ptr(), _stream())
+    plan = FusedPlan(N, list(totals), dense_items, dense_rel, tile_base, pos_win, order_s, wstart_s, sparse_items, sparse_rel,
+                     order_l, samp, dict(blocks), swin)
+    plan._totals_dev = totals_dev
+    return plan
+
+
+
 @dataclass
 class PairIndex:
     """CSR pair list of one block parity.  All index tensors are int32 on the device."""
@@ -35,6 +151,7 @@ class PairIndex:
     row_order: torch.Tensor | None = None  # [N]   points sorted by window (locality hint for the fused entry points)
     win_offsets: torch.Tensor | None = None  # [n_win+1] window boundaries inside row_order
     n_win: int = 0
+    plan: FusedPlan | None = None           # work plan of the fused kernels (build_stratified_index(..., fused=True))
     _fused: tuple | None = field(default=None, repr=False)   # (flags u8 [n_win], fallback_rows i32 [count])
     _tcsr: ext.TransposedCSR | None = field(default=None, repr=False)
     _packed: dict = field(default_factory=dict, repr=False)   # L -> (rel_packed, t_rel_packed | None)
@@ -42,7 +159,7 @@ class PairIndex:
 
     @property
     def N(self) -> int:
-        return self.index_0_offsets.numel() - 1
+        return self.index_0_offsets.numel() - 1 if self.index_0_offsets is not None else self.plan.N
 
     @property
     def tcsr(self) -> ext.TransposedCSR:
@@ -118,9 +235,12 @@ def fps_new_offset(offset: torch.Tensor, downsample_scale: int) -> torch.Tensor:
 
 def build_stratified_index(xyz: torch.Tensor, offset: torch.Tensor, window_size: float, quant_size: float | None,
                            downsample_idx: torch.Tensor | None, parity: int, want_index_0: bool = False,
-                           workspace: torch.Tensor | None = None) -> PairIndex:
+                           workspace: torch.Tensor | None = None, fused: bool = False, csr: bool = True,
+                           swin_shift: float | None = None) -> PairIndex:
     """One block parity of `get_indice_pairs` + sort + CSR (+ rel-pos index when quant_size is given).
-    downsample_idx=None gives dense window pairs only (the Swin / 3DSwin variant)."""
+    downsample_idx=None gives dense window pairs only (the Swin / 3DSwin variant).
+    fused=True also builds the work plan of the fused kernels (`PairIndex.plan`); csr=False then skips the M-sized CSR
+    arrays, which only the per-op entry points need.  swin_shift: the plan carries the 3DSwin rel-pos index."""
     if not (xyz.is_cuda and xyz.dtype == torch.float32 and xyz.is_contiguous() and xyz.dim() == 2 and xyz.shape[1] == 3):
         raise TypeError("xyz must be a contiguous CUDA float32 [N,3] tensor")
     N, b = xyz.shape[0], offset.numel()
@@ -140,9 +260,19 @@ def build_stratified_index(xyz: torch.Tensor, offset: torch.Tensor, window_size:
     _cabi.call("stb200_stratified_pairs_count", N, b, xyz.data_ptr(), offset.data_ptr(), float(window_size),
                int(parity) & 1, ds_ptr, m, workspace.data_ptr(), workspace.numel(), offsets.data_ptr(),
                totals.data_ptr(), _stream())
-    M, n_max, err, n_win = totals.tolist()      # the one host sync: the caller has to allocate M-sized outputs
+    plan_part = _plan_count(N, m > 0, workspace, FUSED_BLOCKS) if fused else None
+    if fused:
+        both = torch.cat([totals, plan_part[1]]).tolist()      # the one host sync: the caller has to allocate the outputs
+        (M, n_max, err, n_win), ptot = both[:4], both[4:]
+    else:
+        M, n_max, err, n_win = totals.tolist()
     if err:
         raise _cabi.Stb200Error("pair builder: window grid has more than 2^32 cells (window too small for the scene extent)")
+    plan = None
+    if fused:
+        plan = _plan_fill(N, xyz, window_size, quant_size, n_win, m, workspace, plan_part[0], plan_part[1], ptot, FUSED_BLOCKS, swin_shift)
+        if not csr:
+            return PairIndex(None, None, None, int(n_max), int(M), None, plan.order_s, plan.wstart_s, int(n_win), plan)
     index_1 = torch.empty(M, dtype=torch.int32, device=dev)
     rel_idx = torch.empty(M, 3, dtype=torch.int32, device=dev) if quant_size is not None else None
     index_0 = torch.empty(M, dtype=torch.int32, device=dev) if want_index_0 else None
@@ -155,7 +285,7 @@ def build_stratified_index(xyz: torch.Tensor, offset: torch.Tensor, window_size:
                    None if rel_idx is None else rel_idx.data_ptr(), None if index_0 is None else index_0.data_ptr(),
                    row_order.data_ptr(), win_offsets.data_ptr(), n_win, M, _stream())
     return PairIndex(offsets, index_1, rel_idx, int(n_max), int(M), index_0, row_order if M else None,
-                     win_offsets if M else None, int(n_win) if M else 0)
+                     win_offsets if M else None, int(n_win) if M else 0, plan)
 
 
 def rel_pos_index_stratified(xyz, index_0_offsets, index_1, window_size: float, quant_size: float) -> torch.Tensor:
@@ -192,7 +322,8 @@ class LayerIndex:
 
 
 def build_layer_index(xyz: torch.Tensor, offset: torch.Tensor, window_size: float, quant_size: float,
-                      downsample_scale: int | None, want_index_0: bool = False, parities=(0, 1)) -> LayerIndex:
+                      downsample_scale: int | None, want_index_0: bool = False, parities=(0, 1), fused: bool = False,
+                      csr: bool = True) -> LayerIndex:
     """stratified_transformer.py:267-317 for one layer: FPS (n_i // ds + 1 samples per scene), then both parities.
     downsample_scale=None -> dense-only pairs (Swin)."""
     offset = offset.to(device=xyz.device, dtype=torch.int32)
@@ -200,7 +331,7 @@ def build_layer_index(xyz: torch.Tensor, offset: torch.Tensor, window_size: floa
     if downsample_scale is not None:
         ds_idx = pointops.furthestsampling(xyz, offset, fps_new_offset(offset, downsample_scale))
     ws = torch.empty(_cabi.load().stb200_pair_builder_workspace_bytes(xyz.shape[0]), dtype=torch.uint8, device=xyz.device)
-    built = {p: build_stratified_index(xyz, offset, window_size, quant_size, ds_idx, p, want_index_0, ws) for p in parities}
+    built = {p: build_stratified_index(xyz, offset, window_size, quant_size, ds_idx, p, want_index_0, ws, fused, csr) for p in parities}
     return LayerIndex(ds_idx, tuple(built.get(p) for p in (0, 1)))
 
 
@@ -212,8 +343,10 @@ def build_layer_index(xyz: torch.Tensor, offset: torch.Tensor, window_size: floa
 # split off: `start` enqueues everything up to the per-query counts without blocking the host, `finish` blocks on
 # an event that has usually fired long ago, then enqueues the fill / transposed CSR / packing kernels.
 class PendingLayerIndex:
-    def __init__(self, xyz, offset, window_size, quant_size, downsample_scale, offset_host, want_index_0=False, L=None):
+    def __init__(self, xyz, offset, window_size, quant_size, downsample_scale, offset_host, want_index_0=False, L=None,
+                 fused=False, csr=True):
         self.xyz, self.window_size, self.quant_size, self.want_index_0, self.L = xyz, window_size, quant_size, want_index_0, L
+        self.fused, self.csr = fused, csr or not fused
         dev = xyz.device
         N, b = xyz.shape[0], len(offset_host)
         self.N = N
@@ -238,9 +371,12 @@ class PendingLayerIndex:
             _cabi.call("stb200_stratified_pairs_count", N, b, xyz.data_ptr(), offset.data_ptr(), float(window_size), parity,
                        None if self.ds_idx is None else self.ds_idx.data_ptr(), m, ws.data_ptr(), nbytes, offsets.data_ptr(),
                        totals.data_ptr(), _stream())
-            host = torch.empty(4, dtype=torch.int32, pin_memory=True)
-            host.copy_(totals, non_blocking=True)
-            self.parts.append((ws, offsets, totals, host))
+            plan_part = _plan_count(N, m > 0, ws, FUSED_BLOCKS) if fused else None
+            host = torch.empty(44 if fused else 4, dtype=torch.int32, pin_memory=True)
+            host[:4].copy_(totals, non_blocking=True)
+            if fused:
+                host[4:].copy_(plan_part[1], non_blocking=True)
+            self.parts.append((ws, offsets, totals, host, plan_part))
         self.m = m
         self.offset = offset
         self.counted = torch.cuda.current_stream().record_event()
@@ -250,10 +386,18 @@ class PendingLayerIndex:
         self.counted.synchronize()
         dev = self.xyz.device
         built = []
-        for ws, offsets, totals, host in self.parts:
-            M, n_max, err, n_win = host.tolist()
+        for ws, offsets, totals, host, plan_part in self.parts:
+            hl = host.tolist()
+            M, n_max, err, n_win = hl[:4]
             if err:
                 raise _cabi.Stb200Error("pair builder: window grid has more than 2^32 cells")
+            plan = None
+            if self.fused:
+                plan = _plan_fill(self.N, self.xyz, self.window_size, self.quant_size, n_win, self.m, ws, plan_part[0], plan_part[1],
+                                  hl[4:], FUSED_BLOCKS)
+                if not self.csr:
+                    built.append(PairIndex(None, None, None, int(n_max), int(M), None, plan.order_s, plan.wstart_s, int(n_win), plan))
+                    continue
             index_1 = torch.empty(M, dtype=torch.int32, device=dev)
             rel_idx = torch.empty(M, 3, dtype=torch.int32, device=dev)
             index_0 = torch.empty(M, dtype=torch.int32, device=dev) if self.want_index_0 else None
@@ -265,8 +409,8 @@ class PendingLayerIndex:
                            index_1.data_ptr(), rel_idx.data_ptr(), None if index_0 is None else index_0.data_ptr(),
                            row_order.data_ptr(), win_offsets.data_ptr(), n_win, M, _stream())
             pi = PairIndex(offsets, index_1, rel_idx, int(n_max), int(M), index_0, row_order if M else None,
-                           win_offsets if M else None, int(n_win) if M else 0)
-            if self.L is not None:
+                           win_offsets if M else None, int(n_win) if M else 0, plan)
+            if self.L is not None and not self.fused:
                 pi.c_struct(self.L, backward=True)   # transposed CSR + packed bins, eagerly, on this stream
             built.append(pi)
         self.parts = None
@@ -279,6 +423,8 @@ def record_stream(li: "LayerIndex", stream) -> None:
     """Tell the caching allocator that `stream` consumes the index tensors (they were allocated on another stream)."""
     for pi in li.parity:
         ts = [pi.index_0_offsets, pi.index_1, pi.rel_idx, pi.index_0, pi.row_order, pi.win_offsets]
+        if pi.plan is not None:
+            ts += pi.plan.tensors()
         if pi._fused is not None:
             ts += list(pi._fused)
         if pi._tcsr is not None:
@@ -306,8 +452,9 @@ class GeometryPrefetcher:
             pf.complete()                             # host: wait for the counts, enqueue fill / transpose / pack
     """
 
-    def __init__(self, layer_cfgs, device=None):
+    def __init__(self, layer_cfgs, device=None, fused=False, csr=True):
         self.cfgs = layer_cfgs
+        self.fused, self.csr = fused, csr
         # stream priority of the geometry work relative to the attention stream (0 = default, -1 = higher)
         self.side = torch.cuda.Stream(device=device, priority=int(os.environ.get("STB200_SIDE_PRIORITY", "0")))
         self.pending = None
@@ -317,7 +464,7 @@ class GeometryPrefetcher:
         main = torch.cuda.current_stream()
         self.side.wait_stream(main)           # inputs produced on the main stream are visible
         with torch.cuda.stream(self.side):
-            self.pending = [PendingLayerIndex(x, o, w, q, ds, oh, L=L)
+            self.pending = [PendingLayerIndex(x, o, w, q, ds, oh, L=L, fused=self.fused, csr=self.csr)
                             for x, o, oh, (w, q, ds, L) in zip(xyzs, offsets, offsets_host, self.cfgs)]
         for x in xyzs:
             x.record_stream(self.side)

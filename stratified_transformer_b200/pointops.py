@@ -332,6 +332,55 @@ def window_attention_fused(q, k, v, table_q, table_k, table_v, pair_index):
     return WindowAttentionFused.apply(q, k, v, table_q, table_k, table_v, pair_index)
 
 
+class WindowAttentionPlan(Function):
+    """The whole pair path of WindowAttention.forward (model/stratified_transformer.py:183-210) and its backward on the
+    window-centric fused kernels (include/stb200.h, "Window-centric fused attention"):
+    out = softmax_seg(q.k + rel-pos bias) applied to (v + rel-pos value), no [M,h] tensor in either direction; the forward
+    keeps only the output and the log-sum-exp of every (query, head) row.  `plan` is a stratified_transformer_b200.index.FusedPlan."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, q, k, v, table_q, table_k, table_v, plan):
+        _contig(q, k, v, table_q, table_k, table_v)
+        N, h, d = q.shape
+        if d != 16:
+            raise ValueError("fused window attention supports head dim 16 (use the per-op entry points otherwise)")
+        L = table_q.shape[0]
+        passes, n_passes = plan.passes(L)
+        out = torch.empty(N, h, d, dtype=torch.float32, device=q.device)
+        lse = torch.empty(N, h, dtype=torch.float32, device=q.device)
+        lsum = torch.empty(N, h, dtype=torch.float32, device=q.device)
+        _cabi.call("stb200_fused_attention_forward", passes, n_passes, N, h, L, q.data_ptr(), k.data_ptr(), v.data_ptr(),
+                   table_q.data_ptr(), table_k.data_ptr(), table_v.data_ptr(), out.data_ptr(), lse.data_ptr(), lsum.data_ptr(),
+                   torch.cuda.current_stream().cuda_stream)
+        ctx.save_for_backward(q, k, v, table_q, table_k, table_v, out, lse)
+        ctx.plan = plan
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, grad_out):
+        q, k, v, table_q, table_k, table_v, out, lse = ctx.saved_tensors
+        plan = ctx.plan
+        N, h, d = q.shape
+        L = table_q.shape[0]
+        passes, n_passes = plan.passes(L)
+        grad_out = grad_out.contiguous()
+        gq = torch.empty_like(q)
+        alloc = torch.zeros_like if plan.needs_zeroed_key_grads else torch.empty_like
+        gk, gv = alloc(k), alloc(v)
+        gtq, gtk, gtv = torch.zeros_like(table_q), torch.zeros_like(table_k), torch.zeros_like(table_v)
+        _cabi.call("stb200_fused_attention_backward", passes, n_passes, N, h, L, grad_out.data_ptr(), out.data_ptr(), lse.data_ptr(),
+                   q.data_ptr(), k.data_ptr(), v.data_ptr(), table_q.data_ptr(), table_k.data_ptr(), table_v.data_ptr(),
+                   gq.data_ptr(), gk.data_ptr(), gv.data_ptr(), gtq.data_ptr(), gtk.data_ptr(), gtv.data_ptr(),
+                   torch.cuda.current_stream().cuda_stream)
+        return gq, gk, gv, gtq, gtk, gtv, None
+
+
+def window_attention_plan(q, k, v, table_q, table_k, table_v, plan):
+    return WindowAttentionPlan.apply(q, k, v, table_q, table_k, table_v, plan)
+
+
 @torch.no_grad()
 def window_attention_inference_bf16(q, k, v, table_q, table_k, table_v, pair_index):
     """Forward-only pair path with bf16 storage of q / k / v and of the staged tables (BASELINE config 3, inference):

@@ -58,7 +58,7 @@ class WindowAttention(nn.Module):
             off32 = index_0_offsets.int().contiguous()
             i1_32 = index_1.int().contiguous()
             idx = PairIndex(off32, i1_32, None, 0, int(index_1.shape[0]), index_0.int().contiguous())
-        if idx.rel_idx is None:
+        if idx.rel_idx is None and idx.index_1 is not None:
             idx.rel_idx = rel_pos_index_stratified(xyz, idx.index_0_offsets, idx.index_1, self.window_size, self.quant_size)
         N, C = feats.shape
         h = self.num_heads
@@ -69,6 +69,16 @@ class WindowAttention(nn.Module):
         query = torch.nn.functional.linear(feats, Wm[:C] * self.scale, None if bm is None else bm[:C] * self.scale).view(N, h, C // h)
         key = torch.nn.functional.linear(feats, Wm[C:2 * C], None if bm is None else bm[C:2 * C]).view(N, h, C // h)
         value = torch.nn.functional.linear(feats, Wm[2 * C:], None if bm is None else bm[2 * C:]).view(N, h, C // h)
+        if idx.plan is not None and self.rel_query and self.rel_key and self.rel_value and C // h == 16 and \
+                not getattr(self, "per_op", False):
+            # window-centric fused kernels: the whole pair path (logits + rel-pos bias + softmax + aggregation, and its
+            # backward) without any [M,h] tensor; available whenever the index came from the device builder with a plan
+            x = pointops.window_attention_plan(query.float(), key.float(), value.float(), self.relative_pos_query_table.float(),
+                                               self.relative_pos_key_table.float(), self.relative_pos_value_table.float(), idx.plan)
+            x = x.view(N, C)
+            if not torch.is_autocast_enabled():
+                x = x.to(self.proj.weight.dtype)
+            return self.proj_drop(self.proj(x))
         off, i1, rel = idx.index_0_offsets, idx.index_1, idx.rel_idx
         if getattr(self, "fused_forward", False) and self.rel_query and self.rel_key and self.rel_value:
             # opt-in (module.fused_forward = True): whole pair path in one op, per-window tensor-core kernel where the

@@ -1,0 +1,51 @@
+"""tcgen05 building blocks (-m gpu): 3xTF32 GEMMs through tensor memory against an fp64 product, for every operand
+interpretation the fused kernels use (csrc/tc_umma.cuh): the same chunked bytes read K-major and MN-major, M = 128 and 64."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def run(mode, M, N, K, seed=0):
+    from stratified_transformer_b200 import _cabi
+    g = torch.Generator().manual_seed(seed)
+    a_shape = (K, M) if mode == 1 else (M, K)
+    b_shape = (K, N) if mode in (1, 2) else (N, K)
+    A = torch.randn(*a_shape, generator=g)
+    B = torch.randn(*b_shape, generator=g)
+    Ad, Bd = A.double(), B.double()
+    want = Ad @ Bd.T if mode == 0 else (Ad.T @ Bd if mode == 1 else Ad @ Bd)
+    out = torch.full((128, N), float("nan"), device="cuda")
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _cabi.call("stb200_tc_selftest", mode, M, N, K, A.cuda().data_ptr(), B.cuda().data_ptr(), out.data_ptr(), status.data_ptr(),
+               torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert int(status.item()) == 0, "MMA never completed (mbarrier timeout)"
+    return out.cpu().double(), want
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("shape", [(128, 112, 16), (128, 16, 112), (128, 64, 64), (128, 192, 16), (128, 16, 64), (128, 240, 16)])
+def test_gemm_3xtf32_m128(mode, shape):
+    M, N, K = shape
+    got, want = run(mode, M, N, K)
+    err = (got[:M] - want).abs().max().item()
+    scale = want.abs().max().item()
+    print(f"mode {mode} {shape}: max err {err:.3e} (scale {scale:.1f})")
+    assert err <= 2e-6 * max(scale, 1.0) * max(1.0, K / 16), f"mode {mode} {shape}: max err {err:.3e}"
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_m64_accumulator_layout(mode):
+    """where the 64 rows of an M = 64 accumulator live in TMEM (documented in tc_umma.cuh)"""
+    M, N, K = 64, 32, 16
+    got, want = run(mode, M, N, K)
+    lanes = []
+    for r in range(M):
+        d = (got - want[r]).abs().max(1).values
+        d = torch.nan_to_num(d, nan=1e9)
+        lanes.append(int(d.argmin()))
+        assert float(d.min()) < 1e-4, f"row {r} not found in TMEM"
+    print("M=64 row -> lane:", lanes)
+    assert lanes == list(range(64)) or lanes == [32 * (r // 16) + r % 16 for r in range(64)], lanes

@@ -18,7 +18,8 @@ def run(mode, M, N, K, seed=0):
     want = Ad @ Bd.T if mode == 0 else (Ad.T @ Bd if mode == 1 else Ad @ Bd)
     out = torch.full((128, N), float("nan"), device="cuda")
     status = torch.zeros(1, dtype=torch.int32, device="cuda")
-    _cabi.call("stb200_tc_selftest", mode, M, N, K, A.cuda().data_ptr(), B.cuda().data_ptr(), out.data_ptr(), status.data_ptr(),
+    A_dev, B_dev = A.cuda().contiguous(), B.cuda().contiguous()   # keep the device copies alive across the call
+    _cabi.call("stb200_tc_selftest", mode, M, N, K, A_dev.data_ptr(), B_dev.data_ptr(), out.data_ptr(), status.data_ptr(),
                torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     assert int(status.item()) == 0, "MMA never completed (mbarrier timeout)"

@@ -81,6 +81,7 @@ struct PassParams {
     const float *g, *lse;           // backward: grad_out [N,h,16], LSE [N,h] (= m of the forward), out = forward output
     float *gq, *gk, *gv;            // [N,h,16]
     float *gtq, *gtk, *gtv;         // [L,h,16,3], accumulated into
+    int dbg;                        // development switches (STB200_FUSED_DBG), 0 in production
 };
 
 struct Layout {   // offsets in floats into the CTA's shared memory

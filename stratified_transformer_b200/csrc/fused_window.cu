@@ -6,6 +6,10 @@
 // to one head (its three table slices stay in shared memory) and striding over the pass's work items.
 #include "common.cuh"
 #include "fused_phases.cuh"
+#include "fused_tc.cuh"
+
+#include <cstdlib>
+#include <cstring>
 
 namespace stb200 {
 
@@ -20,6 +24,54 @@ __global__ void __launch_bounds__(fw::NT, 1) fused_window_kernel(const PassParam
 }
 
 constexpr size_t kMaxSmem = 232448;   // 227 KB opt-in limit per CTA on sm_100a
+
+// tensor-core version (fused_tc.cuh): 512 threads, 512 TMEM columns per CTA, one mbarrier for MMA completion
+template <int BQ, int BK, int HRT, bool BWD>
+__global__ void __launch_bounds__(fwtc::NTC, 1) fused_window_tc_kernel(const PassParams P, int ctas_per_head) {
+    extern __shared__ __align__(128) unsigned char fw_smem_tc[];
+    const fwtc::TcLayout y = fwtc::make_tc_layout(BQ, BK, P.Rpad, BWD);
+    uint32_t *slot = reinterpret_cast<uint32_t *>(fw_smem_tc + y.slot);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(fw_smem_tc + y.slot + 8);
+    const int head = blockIdx.x / ctas_per_head, cta = blockIdx.x - head * ctas_per_head;
+    if (threadIdx.x < 32) tc::tmem_alloc(slot, fwtc::TMEM_COLS);
+    if (threadIdx.x == 0) tc::mbar_init(bar, 1);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    fwtc::TcCtx ctx{*slot, tc::smem_u32(fw_smem_tc), bar, 0u};
+    if (BWD) fwtc::backward_cta_tc<BQ, BK, HRT>(P, head, cta, ctas_per_head, fw_smem_tc, ctx);
+    else fwtc::forward_cta_tc<BQ, BK>(P, head, cta, ctas_per_head, fw_smem_tc, ctx);
+    tc::fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x < 32) tc::tmem_dealloc(ctx.tmem, fwtc::TMEM_COLS);
+}
+
+// STB200_FUSED_IMPL = fma: always the FMA kernels (A/B measurements); default: tensor-core kernels whenever they fit
+static bool use_tc() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = std::getenv("STB200_FUSED_IMPL");
+        v = (e && !std::strcmp(e, "fma")) ? 0 : 1;
+    }
+    return v == 1;
+}
+
+template <int BQ, int BK, int HRT, bool BWD>
+static int launch_pass_tc(const PassParams &P, const char *name, double bytes, cudaStream_t s) {
+    const size_t smem = fwtc::make_tc_layout(BQ, BK, P.Rpad, BWD).total;
+    static bool attr_set = false;
+    if (!attr_set) {
+        const cudaError_t e = cudaFuncSetAttribute(fused_window_tc_kernel<BQ, BK, HRT, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+        STB200_REQUIRE(e == cudaSuccess, STB200_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    int per_head = kNumSMs / P.h;
+    if (per_head < 1) per_head = 1;
+    if (per_head > P.n_items) per_head = P.n_items;
+    KernelScope ks(name, bytes, s);
+    fused_window_tc_kernel<BQ, BK, HRT, BWD><<<per_head * P.h, fwtc::NTC, smem, s>>>(P, per_head);
+    return STB200_OK;
+}
 
 template <int BQ, int BK, bool BWD>
 static int launch_pass(const PassParams &P, const char *name, double bytes, cudaStream_t s) {
@@ -49,8 +101,16 @@ static int dispatch_pass(const stb200_fused_pass &ps, PassParams &P, const char 
     P.q_order = ps.q_order; P.k_order = ps.k_order; P.rel = ps.rel;
     P.pos_win = ps.pos_win; P.wstart = ps.wstart; P.tile_base = ps.tile_base;
     P.bin_lo = ps.bin_lo; P.RB = ps.RB;
-    P.Rpad = (3 * ps.RB + 7) / 8 * 8;
+    { const char *e = std::getenv("STB200_FUSED_DBG"); P.dbg = e ? std::atoi(e) : 0; }
+    P.Rpad = (3 * ps.RB + 15) / 16 * 16;
     STB200_REQUIRE(ps.RB > 0 && P.Rpad <= 256, STB200_ERR_ARG, "fused window attention stages at most 85 bins per axis (got %d)", ps.RB);
+    if (use_tc()) {   // tensor-core kernels where their shared-memory plan fits (S3DIS table length: both passes)
+        const int hr = fwtc::hist_rows(P.Rpad);
+        if (ps.BQ == 64 && ps.BK == 64 && hr == 128 && fwtc::make_tc_layout(64, 64, P.Rpad, BWD).total <= kMaxSmem)
+            return launch_pass_tc<64, 64, 128, BWD>(P, name, bytes, s);
+        if (ps.BQ == 48 && ps.BK == 32 && hr == 192 && fwtc::make_tc_layout(48, 32, P.Rpad, BWD).total <= kMaxSmem)
+            return launch_pass_tc<48, 32, 192, BWD>(P, name, bytes, s);
+    }
     if (ps.BQ == 64 && ps.BK == 64) return launch_pass<64, 64, BWD>(P, name, bytes, s);
     if (ps.BQ == 48 && ps.BK == 32) return launch_pass<48, 32, BWD>(P, name, bytes, s);
     if (ps.BQ == 32 && ps.BK == 32) return launch_pass<32, 32, BWD>(P, name, bytes, s);

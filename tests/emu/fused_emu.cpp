@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "../../stratified_transformer_b200/csrc/fused_phases.cuh"
+#include "../../stratified_transformer_b200/csrc/fused_tc.cuh"
 
 using namespace stb200::fw;
 
@@ -31,6 +32,44 @@ extern "C" int fw_emu_run(const PassParams *P, int BQ, int BK, int backward, int
     else if (BQ == 32 && BK == 32) run<32, 32>(*P, backward, n_cta);
     else if (BQ == 16 && BK == 16) run<16, 16>(*P, backward, n_cta);
     else if (BQ == 16 && BK == 8) run<16, 8>(*P, backward, n_cta);
+    else return 1;
+    return 0;
+}
+
+// ---- tensor-core version (fused_tc.cuh): TMEM and the MMAs are emulated functionally -------------------------------------
+using namespace stb200::fwtc;
+
+template <int BQ, int BK>
+static void run_tc(const PassParams &P, int backward, int n_cta) {
+    const TcLayout y = make_tc_layout(BQ, BK, P.Rpad, backward != 0);
+    unsigned char *sm = (unsigned char *)aligned_alloc(128, y.total);
+    float *tmem = (float *)malloc(sizeof(float) * 128 * TMEM_COLS);
+    for (int head = 0; head < P.h; ++head)
+        for (int cta = 0; cta < n_cta; ++cta) {
+            for (uint32_t i = 0; i < y.total / 4; ++i) ((float *)sm)[i] = __builtin_nanf("");
+            for (int i = 0; i < 128 * TMEM_COLS; ++i) tmem[i] = __builtin_nanf("");
+            TcCtx ctx{tmem, sm};
+            if (backward) {
+                if (y.HR == 128) backward_cta_tc<BQ, BK, 128>(P, head, cta, n_cta, sm, ctx);
+                else if (y.HR == 192) backward_cta_tc<BQ, BK, 192>(P, head, cta, n_cta, sm, ctx);
+                else backward_cta_tc<BQ, BK, 256>(P, head, cta, n_cta, sm, ctx);
+            } else {
+                forward_cta_tc<BQ, BK>(P, head, cta, n_cta, sm, ctx);
+            }
+        }
+    free(sm);
+    free(tmem);
+}
+
+extern "C" int fw_emu_tc_smem_bytes(int BQ, int BK, int Rpad, int backward) { return (int)make_tc_layout(BQ, BK, Rpad, backward != 0).total; }
+
+extern "C" int fw_emu_run_tc(const PassParams *P, int BQ, int BK, int backward, int n_cta) {
+    if (P->Rpad % 16) return 2;
+    if (BQ == 64 && BK == 64) run_tc<64, 64>(*P, backward, n_cta);
+    else if (BQ == 48 && BK == 32) run_tc<48, 32>(*P, backward, n_cta);
+    else if (BQ == 32 && BK == 32) run_tc<32, 32>(*P, backward, n_cta);
+    else if (BQ == 16 && BK == 16) run_tc<16, 16>(*P, backward, n_cta);
+    else if (BQ == 16 && BK == 8) run_tc<16, 8>(*P, backward, n_cta);
     else return 1;
     return 0;
 }

@@ -33,7 +33,7 @@ class PassParams(ctypes.Structure):
                 ("out", ctypes.c_void_p), ("m", ctypes.c_void_p), ("l", ctypes.c_void_p),
                 ("g", ctypes.c_void_p), ("lse", ctypes.c_void_p),
                 ("gq", ctypes.c_void_p), ("gk", ctypes.c_void_p), ("gv", ctypes.c_void_p),
-                ("gtq", ctypes.c_void_p), ("gtk", ctypes.c_void_p), ("gtv", ctypes.c_void_p)]
+                ("gtq", ctypes.c_void_p), ("gtk", ctypes.c_void_p), ("gtv", ctypes.c_void_p), ("dbg", ctypes.c_int)]
 
 
 @pytest.fixture(scope="module")
@@ -41,11 +41,12 @@ def emu():
     if not os.path.isdir(CUDA_INC):
         pytest.skip("CUDA headers not available")
     os.makedirs(os.path.dirname(EMU_LIB), exist_ok=True)
-    hdr = os.path.join(ROOT, "stratified_transformer_b200", "csrc", "fused_phases.cuh")
-    if not os.path.exists(EMU_LIB) or os.path.getmtime(EMU_LIB) < max(os.path.getmtime(EMU_SRC), os.path.getmtime(hdr)):
+    hdrs = [os.path.join(ROOT, "stratified_transformer_b200", "csrc", n) for n in ("fused_phases.cuh", "fused_tc.cuh", "tc_umma.cuh")]
+    if not os.path.exists(EMU_LIB) or os.path.getmtime(EMU_LIB) < max([os.path.getmtime(EMU_SRC)] + [os.path.getmtime(x) for x in hdrs]):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", CUDA_INC, EMU_SRC, "-o", EMU_LIB])
     lib = ctypes.CDLL(EMU_LIB)
     lib.fw_emu_run.argtypes = [ctypes.POINTER(PassParams), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.fw_emu_run_tc.argtypes = [ctypes.POINTER(PassParams), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     return lib
 
 
@@ -59,10 +60,10 @@ def bin_range(L, dense, swin=False):
         lo, RB = 0, L
     else:
         lo, RB = max(L // 4 - 2, 0), (L + 1) // 2 + 4
-    return lo, RB, (3 * RB + 7) // 8 * 8
+    return lo, RB, (3 * RB + 15) // 16 * 16
 
 
-def run_pass(lib, part, ord_idx, backward, arrays, h, L, dense, swin=False, n_cta=3):
+def run_pass(lib, part, ord_idx, backward, arrays, h, L, dense, swin=False, n_cta=3, tc=False):
     off = int(part["counts"][:ord_idx].sum())
     cnt = int(part["counts"][ord_idx])
     if cnt == 0:
@@ -76,10 +77,11 @@ def run_pass(lib, part, ord_idx, backward, arrays, h, L, dense, swin=False, n_ct
     P.bin_lo, P.RB, P.Rpad, P.L, P.h = lo, RB, Rpad, L, h
     for name in ("q", "k", "v", "tq", "tk", "tv", "out", "m", "l", "g", "lse", "gq", "gk", "gv", "gtq", "gtk", "gtv"):
         setattr(P, name, ptr(arrays.get(name)))
-    assert lib.fw_emu_run(ctypes.byref(P), part["BQ"], part["BK"], int(backward), n_cta) == 0
+    fn = lib.fw_emu_run_tc if tc else lib.fw_emu_run
+    assert fn(ctypes.byref(P), part["BQ"], part["BK"], int(backward), n_cta) == 0
 
 
-def fused_forward_backward(lib, plan, q, k, v, tq, tk, tv, g, swin=False):
+def fused_forward_backward(lib, plan, q, k, v, tq, tk, tv, g, swin=False, tc=False):
     N, h, _ = q.shape
     L = tq.shape[0]
     A = dict(q=q, k=k, v=v, tq=tq, tk=tk, tv=tv, g=g)
@@ -87,10 +89,10 @@ def fused_forward_backward(lib, plan, q, k, v, tq, tk, tv, g, swin=False):
     A["m"] = np.full((N, h), np.nan, np.float32)
     A["l"] = np.full((N, h), np.nan, np.float32)
     for o in range(fpo.MAXORD):
-        run_pass(lib, plan["dense"], o, False, A, h, L, True, swin)
+        run_pass(lib, plan["dense"], o, False, A, h, L, True, swin, tc=tc)
     if plan["sparse"] is not None:
         for o in range(fpo.MAXORD):
-            run_pass(lib, plan["sparse"], o, False, A, h, L, False)
+            run_pass(lib, plan["sparse"], o, False, A, h, L, False, tc=tc)
     A["lse"] = A["m"]
     chunked = plan["dense"]["max_win"] > plan["dense"]["BK"]
     fill = 0.0 if chunked else np.nan     # key rows of chunked windows are accumulated into: the caller zero-fills
@@ -100,10 +102,10 @@ def fused_forward_backward(lib, plan, q, k, v, tq, tk, tv, g, swin=False):
     for name, t in (("gtq", tq), ("gtk", tk), ("gtv", tv)):
         A[name] = np.zeros_like(t)
     for o in range(fpo.MAXORD):
-        run_pass(lib, plan["dense"], o, True, A, h, L, True, swin)
+        run_pass(lib, plan["dense"], o, True, A, h, L, True, swin, tc=tc)
     if plan["sparse"] is not None:
         for o in range(fpo.MAXORD):
-            run_pass(lib, plan["sparse"], o, True, A, h, L, False)
+            run_pass(lib, plan["sparse"], o, True, A, h, L, False, tc=tc)
     return A
 
 
@@ -144,9 +146,10 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("tc", [False, True], ids=["fma", "tcgen05"])
 @pytest.mark.parametrize("case", CASES)
 @pytest.mark.parametrize("parity", [0, 1])
-def test_emulated_kernels_match_oracle(emu, case, parity):
+def test_emulated_kernels_match_oracle(emu, case, parity, tc):
     n_pts, window, quant, BQ, BK, BQS, BKS, h, lattice = case
     xyz, offset, ds = small_case(n_pts, 11, window, quant, lattice)
     plan = fpo.build(xyz, offset, window, quant, parity, ds, BQ=BQ, BK=BK, BQS=BQS, BKS=BKS)
@@ -160,7 +163,7 @@ def test_emulated_kernels_match_oracle(emu, case, parity):
     tq, tk, tv = (torch.rand(L, h, 16, 3, generator=g) - 0.5 for _ in range(3))   # U(-.5,.5): strong table signal
     want = ao.layer_fwd_bwd(q.double(), k.double(), v.double(), torch.from_numpy(ref["offsets"]), torch.from_numpy(ref["index_1"]),
                             tq.double(), tk.double(), tv.double(), torch.from_numpy(rel_ref), go.double())
-    A = fused_forward_backward(emu, plan, *(t.numpy().copy() for t in (q, k, v, tq, tk, tv, go)))
+    A = fused_forward_backward(emu, plan, *(t.numpy().copy() for t in (q, k, v, tq, tk, tv, go)), tc=tc)
     # log-sum-exp of every row
     i0 = want["i0"]
     s = want["s"]
@@ -176,7 +179,8 @@ def test_emulated_kernels_match_oracle(emu, case, parity):
         assert (err <= tol).all(), f"{name}: max err {err.max():.3e} (|ref| max {np.abs(r).max():.2f})"
 
 
-def test_emulated_swin_dense_only(emu):
+@pytest.mark.parametrize("tc", [False, True], ids=["fma", "tcgen05"])
+def test_emulated_swin_dense_only(emu, tc):
     """3DSwin variant: dense windows only, tables of length 2*int(w/quant)-1, per-point quantised rel-pos index."""
     n_pts, window, quant, h = 600, 0.32, 0.02, 2
     xyz, offset, _ = small_case(n_pts, 21, window, quant)
@@ -194,7 +198,7 @@ def test_emulated_swin_dense_only(emu):
     tq, tk, tv = (torch.rand(L, h, 16, 3, generator=g) - 0.5 for _ in range(3))
     want = ao.layer_fwd_bwd(q.double(), k.double(), v.double(), torch.from_numpy(offsets), torch.from_numpy(i1), tq.double(),
                             tk.double(), tv.double(), torch.from_numpy(rel), go.double())
-    A = fused_forward_backward(emu, plan, *(t.numpy().copy() for t in (q, k, v, tq, tk, tv, go)), swin=True)
+    A = fused_forward_backward(emu, plan, *(t.numpy().copy() for t in (q, k, v, tq, tk, tv, go)), swin=True, tc=tc)
     for name in ("out", "gq", "gk", "gv", "gtq", "gtk", "gtv"):
         r = want[name].numpy()
         err = np.abs(A[name].astype(np.float64) - r)

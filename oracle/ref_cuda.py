@@ -153,3 +153,28 @@ def knnquery(nsample, xyz, new_xyz, offset, new_offset):
     d2 = torch.zeros(m, nsample, device=xyz.device)
     _call("knnquery_cuda_launcher", m, nsample, _p(xyz), _p(new_xyz), _p(offset), _p(new_offset), _p(idx), _p(d2))
     return idx, d2
+
+
+def timed(name, args, reps=10, warmup=2):
+    """Average device time in ms of the reference launcher `name` (same argument convention as _call), measured with
+    CUDA events on the legacy default stream the launchers use (torch's default stream).  bench.py's ref_cuda_baseline leg."""
+    fn = getattr(lib(), name)
+    fn.restype = None
+    conv = []
+    for a in args:
+        if isinstance(a, ctypes.c_void_p):
+            conv.append(a)
+        elif isinstance(a, _U):
+            conv.append(ctypes.c_uint(int(a)))
+        else:
+            conv.append(ctypes.c_int(int(a)))
+    torch.cuda.synchronize()
+    for _ in range(warmup):
+        fn(*conv)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(torch.cuda.default_stream())
+    for _ in range(reps):
+        fn(*conv)
+    e1.record(torch.cuda.default_stream())
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps

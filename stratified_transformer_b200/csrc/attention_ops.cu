@@ -878,7 +878,7 @@ static double seg_bytes(const SegParams &p, int D, int M, bool rows_x, bool rows
     if (weights) b += 4.0 * M * p.h;
     if (gather) b += 4.0 * M;
     if (perm) b += 4.0 * M;
-    if (ntables) b += 12.0 * M + ntables * 12.0 * p.L * C;   // rel_idx + tables
+    if (ntables) b += (p.packed ? 4.0 : 12.0) * M + ntables * 12.0 * p.L * C;   // packed bins (4 B / pair) or rel_idx (12 B / pair) + tables
     b += out_pairs ? 4.0 * M * p.h : 4.0 * N * C * (p.accumulate ? 2 : 1);
     return b;
 }

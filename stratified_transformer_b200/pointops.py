@@ -382,12 +382,13 @@ def window_attention_plan(q, k, v, table_q, table_k, table_v, plan):
 
 
 @torch.no_grad()
-def window_attention_inference_bf16(q, k, v, table_q, table_k, table_v, pair_index):
+def window_attention_inference_bf16(q, k, v, table_q, table_k, table_v, pair_index, pre_cast=False):
     """Forward-only pair path with bf16 storage of q / k / v and of the staged tables (BASELINE config 3, inference):
-    logits and softmax in fp32, output fp32 [N, h, d].  Tolerance vs the fp32 path: 2e-2 of the output scale."""
+    logits and softmax in fp32, output fp32 [N, h, d].  Tolerance vs the fp32 path: 2e-2 of the output scale.
+    pre_cast: q / k / v are already contiguous bf16 tensors (an inference stack keeps them in bf16 from the qkv GEMM)."""
     N, h, d = q.shape
     L = table_q.shape[0]
-    q16, k16, v16 = (t.to(torch.bfloat16).contiguous() for t in (q, k, v))
+    q16, k16, v16 = (q, k, v) if pre_cast else (t.to(torch.bfloat16).contiguous() for t in (q, k, v))
     tq, tk, tv = (t.float().contiguous() for t in (table_q, table_k, table_v))
     ix = pair_index.c_struct(L)
     stream = torch.cuda.current_stream().cuda_stream

@@ -202,3 +202,58 @@ def test_module_plan_path_matches_per_op_path():
         res[mode] = dict(y=y.detach(), gf=f.grad, **{n: p.grad.clone() for n, p in attn.named_parameters()})
     for name in res["plan"]:
         _close(res["plan"][name], res["per_op"][name], 5e-4, name)
+
+
+@pytest.mark.parametrize("level", [0, 1, 2, 3])
+@pytest.mark.parametrize("parity", [0, 1])
+def test_per_op_benched_path_matches_reference_kernels_full_size(hierarchy, level, parity):
+    """The code path bench.py times by default (window_logits / segment_softmax / window_aggregate and their `_ws` backward
+    with packed bins, window row order, transposed CSR and both length orders) on builder-produced indices of one 80k-point
+    scene at the four layer shapes, every output and gradient against the reference's own kernels."""
+    from oracle import ref_cuda
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref/libpointops2_ref.so not built")
+    from stratified_transformer_b200 import index, pointops
+    xd, od = hierarchy[level]
+    window, quant, h = 0.16 * 2 ** level, 0.01 * 2 ** level, 3 * 2 ** level
+    ds = pointops.furthestsampling(xd, od, index.fps_new_offset(od, 8))
+    pi = index.build_stratified_index(xd, od, window, quant, ds, parity)
+    N, L = xd.shape[0], 64
+    g = torch.Generator().manual_seed(17 + level)
+    q, k, v, go = (torch.randn(N, h, 16, generator=g) for _ in range(4))
+    q = q * 0.5
+    tq, tk, tv = ((torch.rand(L, h, 16, 3, generator=g) - 0.5) * 0.2 for _ in range(3))
+    leaves = [t.cuda().requires_grad_(True) for t in (q, k, v, tq, tk, tv)]
+    s = pointops.window_logits(leaves[0], leaves[1], leaves[3], leaves[4], pi)
+    p = pointops.segment_softmax(s, pi.index_0_offsets)
+    out = pointops.window_aggregate(p, leaves[2], leaves[5], pi)
+    out.backward(go.cuda())
+    got = dict(out=out, gq=leaves[0].grad, gk=leaves[1].grad, gv=leaves[2].grad, gtq=leaves[3].grad, gtk=leaves[4].grad, gtv=leaves[5].grad)
+    want = _ref_kernels(pi, q, k, v, tq, tk, tv, go)
+    msgs = [_check(val, want[name], 2e-4 if name.startswith("gt") else 1e-4, f"{name} (level {level}, parity {parity})",
+                   1e-5 if name.startswith("gt") else 0.0) for name, val in got.items()]
+    assert not any(msgs), "; ".join(m for m in msgs if m)
+
+
+@pytest.mark.parametrize("parity", [0, 1])
+def test_swin_invariant_and_window_membership_full_size(hierarchy, parity):
+    """Dense-only pairs at full size (80k points): the reference's own invariant M == (counts**2).sum()
+    (model/swin3d_transformer.py:259,280), and a brute-force check that every emitted pair shares a window id computed in
+    fp64 — except where the fp32 voxel arithmetic of torch_cluster legitimately differs from fp64 at a window boundary."""
+    from stratified_transformer_b200 import index
+    xd, od = hierarchy[0]
+    w = 0.16
+    pi = index.build_stratified_index(xd, od, w, 0.01, None, parity, want_index_0=True)
+    wo = pi.win_offsets.long()
+    counts = wo[1:] - wo[:-1]
+    assert pi.M == int((counts ** 2).sum())
+    x = xd.double().cpu()
+    shift = 0.5 * w if parity else 0.0
+    cell = torch.floor((x + shift - x.min(0).values) / w).long()
+    i0, i1 = pi.index_0.long().cpu(), pi.index_1.long().cpu()
+    differ = (cell[i0] != cell[i1]).any(1)
+    # pairs whose fp64 window ids differ must have an endpoint within a few fp32 ulps of a window boundary
+    frac = ((x + shift - x.min(0).values) / w)
+    near = ((frac - frac.round()).abs() < 1e-5).any(1)
+    assert bool((near[i0[differ]] | near[i1[differ]]).all())
+    assert int(differ.sum()) < 1e-3 * pi.M

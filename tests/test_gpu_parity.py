@@ -246,8 +246,35 @@ def test_v1_ops_vs_oracle():
     gp, gv, gt = ao.step2_rpv_bwd(go.double(), w.double(), d64["v"], i0c, i1c, d64["tq"], relc)
     close(wd.grad, gp, "v1 rpv gp"); close(v.grad, gv, "v1 rpv gv"); close(tq.grad, gt, "v1 rpv gt", tol=2e-4)
 
-    b2 = pointops.dot_prod_with_idx_v2(q.detach(), i0, k.detach(), i1, dev["tq"], dev["tk"], rel)
+    # DotProdWithIdx_v2 (functions/pointops.py:372-443): forward AND backward (q, k and both tables)
+    q2, k2 = dev["q"].clone().requires_grad_(True), dev["k"].clone().requires_grad_(True)
+    tq2, tk2 = dev["tq"].clone().requires_grad_(True), dev["tk"].clone().requires_grad_(True)
+    b2 = pointops.dot_prod_with_idx_v2(q2, i0, k2, i1, tq2, tk2, rel)
     close(b2, ao.rpe_fwd(d64["q"], d64["k"], i0c, i1c, d64["tq"], d64["tk"], relc), "rpe v2")
+    b2.backward(wd.detach())
+    gq2, gk2, gtq2, gtk2 = ao.rpe_bwd(w.double(), d64["q"], d64["k"], i0c, i1c, d64["tq"], d64["tk"], relc)
+    close(q2.grad, gq2, "rpe v2 gq"); close(k2.grad, gk2, "rpe v2 gk")
+    close(tq2.grad, gtq2, "rpe v2 gtq", tol=2e-4); close(tk2.grad, gtk2, "rpe v2 gtk", tol=2e-4)
+
+
+@pytest.mark.skipif(not ref_cuda.available(), reason="oracle/_ref/libpointops2_ref.so not built")
+def test_v1_ops_vs_reference_kernels():
+    """v1 entry points (unsorted explicit index0 / index1) against the reference's own v1 kernels
+    (attention/attention_cuda_kernel.cu, rpe/relative_pos_encoding_cuda_kernel.cu) on the same tensors."""
+    from stratified_transformer_b200 import pointops
+    cpu, dev = make_case(900, 20000, 6, 16, 31, seed=14, empty=False)
+    g = torch.Generator().manual_seed(19)
+    perm = torch.randperm(cpu["i0"].numel(), generator=g)
+    i0, i1, rel = (cpu[n][perm].cuda().int().contiguous() for n in ("i0", "i1", "rel"))
+    N = 900
+    w = torch.rand(i0.numel(), 6, generator=g).cuda()
+    with torch.no_grad():
+        close(pointops.attention_step1(dev["q"], dev["k"], i0, i1), ref_cuda.v1_step1_fwd(dev["q"], dev["k"], i0, i1), "v1 step1 vs ref")
+        n_q = int(i0.max().item()) + 1
+        close(pointops.attention_step2(w, dev["v"], i0, i1), ref_cuda.v1_step2_fwd(w, dev["v"], i0, i1, n_q), "v1 step2 vs ref")
+        close(pointops.dot_prod_with_idx(dev["q"], i0, dev["tq"], rel), ref_cuda.v1_rpe_fwd(dev["q"], i0, dev["tq"], rel), "v1 rpe vs ref")
+        close(pointops.attention_step2_with_rel_pos_value(w, dev["v"], i0, i1, dev["tv"], rel),
+              ref_cuda.v1_step2_rpv_fwd(w, dev["v"], i0, i1, dev["tv"], rel, n_q), "v1 step2 rpv vs ref")
 
 
 def test_scatter_softmax_shim():

@@ -1,5 +1,8 @@
-"""tcgen05 building blocks (-m gpu): 3xTF32 GEMMs through tensor memory against an fp64 product, for every operand
-interpretation the fused kernels use (csrc/tc_umma.cuh): the same chunked bytes read K-major and MN-major, M = 128 and 64."""
+"""tcgen05 building blocks (-m gpu): 3xTF32 GEMMs through tensor memory against an fp64 product for the operand form the
+fused kernels use (csrc/tc_umma.cuh): K-major un-swizzled chunked matrices, M = 128 and 64 (and the TMEM row -> lane map of
+an M = 64 accumulator).  MN-major tf32 operands exist only with the 128B_BASE32B swizzle (CUTLASS: "for mn-major tf32
+operands, SW128_32B is the only available smem layout"); the un-swizzled MN-major modes of the self-test (1, 2) return
+zeros on hardware and are not used by any kernel — the fused kernels keep every operand K-major instead."""
 import numpy as np
 import pytest
 import torch
@@ -26,8 +29,8 @@ def run(mode, M, N, K, seed=0):
     return out.cpu().double(), want
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
-@pytest.mark.parametrize("shape", [(128, 112, 16), (128, 16, 112), (128, 64, 64), (128, 192, 16), (128, 16, 64), (128, 240, 16)])
+@pytest.mark.parametrize("mode", [0])
+@pytest.mark.parametrize("shape", [(128, 16, 32), (128, 16, 8), (128, 112, 16), (128, 16, 112), (128, 64, 64), (128, 192, 16), (128, 16, 64), (128, 240, 16)])
 def test_gemm_3xtf32_m128(mode, shape):
     M, N, K = shape
     got, want = run(mode, M, N, K)
@@ -37,7 +40,7 @@ def test_gemm_3xtf32_m128(mode, shape):
     assert err <= 2e-6 * max(scale, 1.0) * max(1.0, K / 16), f"mode {mode} {shape}: max err {err:.3e}"
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0])
 def test_m64_accumulator_layout(mode):
     """where the 64 rows of an M = 64 accumulator live in TMEM (documented in tc_umma.cuh)"""
     M, N, K = 64, 32, 16
@@ -49,4 +52,4 @@ def test_m64_accumulator_layout(mode):
         lanes.append(int(d.argmin()))
         assert float(d.min()) < 1e-4, f"row {r} not found in TMEM"
     print("M=64 row -> lane:", lanes)
-    assert lanes == list(range(64)) or lanes == [32 * (r // 16) + r % 16 for r in range(64)], lanes
+    assert lanes == [32 * (r // 16) + r % 16 for r in range(64)], lanes

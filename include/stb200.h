@@ -176,6 +176,12 @@ int stb200_stratified_pairs_fill(int N, const float *xyz, float window_size_x2, 
                                  int *win_offsets /* [n_win+1] window boundaries in row_order, may be NULL */, int n_win,
                                  int M, void *stream);
 
+/* Which torch device's arithmetic the Stratified rel-pos index reproduces bit for bit.  1 (default): CUDA tensors, i.e. the
+ * reference as it runs -- `round(r * 1e5) / 1e5` is a multiplication by the fp32 reciprocal there; 0: CPU tensors (IEEE
+ * division), for fixtures generated with CPU torch.  Applies to every later call of this process (pair builder, fused plan,
+ * stb200_rel_pos_index_stratified); synchronises the device. */
+int stb200_set_torch_semantics(int cuda);
+
 /* Relative-position index of an existing CSR pair list.
  * Stratified: idx = ((round((xyz[i0]-xyz[i1])*1e5)/1e5) + 2w - 1e-4) // quant  (stratified_transformer.py:186-188)
  * Swin:       xq = ((xyz - min + shift) % w) // quant; idx = xq[i0] - xq[i1] + qgl - 1 (swin3d_transformer.py:151-154)

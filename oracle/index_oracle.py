@@ -185,11 +185,21 @@ def build_layer_index(xyz, offset, window_size, downsample_scale, downsample_idx
 
 
 # ----------------------------------------------------------------------------- rel-pos index
-def rel_pos_index_stratified(xyz, index_0, index_1, window_size, quant_size):
-    """idx = ((round((xyz[i0]-xyz[i1])*1e5)/1e5) + 2w - 1e-4) // quant, all fp32, -> int32 [M,3]."""
+TORCH_DEVICE = "cuda"   # which torch device's arithmetic rel_pos_index_stratified restates by default (see its docstring)
+
+
+def rel_pos_index_stratified(xyz, index_0, index_1, window_size, quant_size, device=None):
+    """idx = ((round((xyz[i0]-xyz[i1])*1e5)/1e5) + 2w - 1e-4) // quant, all fp32, -> int32 [M,3].
+
+    `/ 100000` is the one operation of the path that torch evaluates differently on the two devices: IEEE division on CPU
+    tensors, multiplication by the fp32 reciprocal on CUDA tensors (ATen's scalar-divisor fast path; measured on the B200
+    box with tools/dbg_torch_cuda_div.py).  device="cuda" (default: the reference only runs on GPUs) / "cpu" (pinned
+    bit for bit against CPU torch in tests/test_oracle_index.py and used for the CPU-generated goldens)."""
+    device = device or TORCH_DEVICE
     xyz = np.asarray(xyz, f32)
     r = (xyz[index_0] - xyz[index_1]).astype(f32)
-    r = (np.rint((r * f32(100000)).astype(f32)).astype(f32) / f32(100000)).astype(f32)
+    r = np.rint((r * f32(100000)).astype(f32)).astype(f32)
+    r = (r * (f32(1) / f32(100000))).astype(f32) if device == "cuda" else (r / f32(100000)).astype(f32)
     t = ((r + f32(2 * window_size)).astype(f32) - f32(0.0001)).astype(f32)
     return floor_div_f32(t, f32(quant_size)).astype(np.int32)
 

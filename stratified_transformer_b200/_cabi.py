@@ -77,6 +77,7 @@ _SIGNATURES = {
     "stb200_fused_attention_forward": [_FP, _c_int, _c_int, _c_int, _c_int] + [P] * 10,
     "stb200_fused_attention_backward": [_FP, _c_int, _c_int, _c_int, _c_int] + [P] * 16,
     "stb200_tc_selftest": [_c_int] * 4 + [P] * 5,
+    "stb200_set_torch_semantics": [_c_int],
     "stb200_rel_pos_index_swin": [_c_int, P, P, P, ctypes.c_float, ctypes.c_float, ctypes.c_float, _c_int, P, P, P, P],
 }
 _RESTYPES = {

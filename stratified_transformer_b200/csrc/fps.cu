@@ -340,6 +340,7 @@ static int ref_block_log2(int n) {
 }
 
 constexpr int kFpsRetrySmallerCluster = -1;
+constexpr int kFpsNotApplicable = -2;   // this (points per thread, CTA size) combination exceeds the register budget: use the streaming kernel
 static long long *g_fps_dbg = nullptr;  // development aid, see stb200_fps_debug_buffer
 
 static int env_int(const char *name, int dflt) {
@@ -350,7 +351,11 @@ static int env_int(const char *name, int dflt) {
 template <int P, int MAXT = (P <= 8 ? 1024 : (P <= 20 ? 512 : 256))>  // register budget: 4 P + ~40 per thread
 static int launch_fps(int b, int cs, int threads, const float *xyz, const int *offset, const int *new_offset, int *idx,
                       int logB, cudaStream_t s) {
-    STB200_REQUIRE(threads <= MAXT && threads % 32 == 0, STB200_ERR_ARG, "fps: %d threads with %d points per thread", threads, P);
+    // The tie order forces cs * threads to be a multiple of the reference's virtual block size, so many small-cluster
+    // configurations (e.g. b = 20 scenes of 30k points: cluster 2 x 512 threads x 30 points) need more threads than the
+    // register budget of P points per thread allows.  Not an error: the caller falls back to the streaming kernel.
+    if (threads > MAXT) return kFpsNotApplicable;
+    STB200_REQUIRE(threads % 32 == 0, STB200_ERR_ARG, "fps: %d threads with %d points per thread", threads, P);
     const size_t smem = (size_t)3 * P * threads * sizeof(float);
     cudaError_t e;
     KernelScope ks("fps_cluster", 0.0, s);  // latency-bound by construction: bytes are not the meaningful unit
@@ -438,6 +443,7 @@ extern "C" int stb200_furthestsampling(int b, int n, const float *xyz, const int
         else if (need <= 32) rc = launch_fps<32>(b, cs, threads, xyz, offset, new_offset, idx, logB, s);
         else if (need <= 40) rc = launch_fps<40>(b, cs, threads, xyz, offset, new_offset, idx, logB, s);
         else break;   // too many points per thread for the register-resident kernel
+        if (rc == kFpsNotApplicable) break;   // a smaller cluster only needs more points per thread
         if (rc != kFpsRetrySmallerCluster) return rc;
     }
     STB200_REQUIRE(tmp, STB200_ERR_ARG, "scene of %d points needs the tmp scratch (streaming path)", n);

@@ -44,9 +44,18 @@ __device__ __forceinline__ float remainder_f32(float a, float b) {  // torch `a 
     return mod;
 }
 
+// `torch.round(rel * 100000) / 100000` (model/stratified_transformer.py:187): on a CUDA tensor torch evaluates a true
+// division by a Python scalar as a multiplication by the fp32 reciprocal (measured on the B200 box, tools/dbg_torch_cuda_div.py:
+// 30 % of the quotients differ from the IEEE division by one ulp, which moves 1 pair in ~20 000 into the neighbouring bin);
+// on a CPU tensor it divides.  The reference only ever runs on the GPU, so the CUDA form is the default; the CPU form
+// (stb200_set_torch_semantics(0)) exists to reproduce fixtures generated with CPU torch.  Nothing else on the path differs
+// between the two devices (floor division and remainder by a scalar, tensor // tensor: 0 mismatches in 2e7 samples).
+__constant__ int c_rel_cuda_division = 1;
+
 __device__ __forceinline__ int rel_index_stratified(float xa, float xb, float two_w, float quant) {
     float r = __fsub_rn(xa, xb);
-    r = __fdiv_rn(rintf(__fmul_rn(r, 100000.f)), 100000.f);
+    r = rintf(__fmul_rn(r, 100000.f));
+    r = c_rel_cuda_division ? __fmul_rn(r, 1.0f / 100000.0f) : __fdiv_rn(r, 100000.f);
     const float t = __fsub_rn(__fadd_rn(r, two_w), 0.0001f);
     return (int)floor_div_f32(t, quant);
 }
@@ -91,6 +100,9 @@ static size_t cub_temp_bytes(int N) {
     cub::DeviceRadixSort::SortPairs(nullptr, a, (const unsigned *)nullptr, (unsigned *)nullptr, (const int *)nullptr,
                                     (int *)nullptr, N, 0, 32);
     cub::DeviceScan::InclusiveSum(nullptr, b, (const int *)nullptr, (int *)nullptr, N + 1);
+    size_t c = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, c, (const int *)nullptr, (int *)nullptr, N + 1);
+    if (c > b) b = c;
     return a > b ? a : b;
 }
 
@@ -648,23 +660,28 @@ int stb200_stratified_pairs_count(int N, int b, const float *xyz, const int *off
     params_kernel<<<1, 32, 0, s>>>(st.mm, st.gp, window_size, parity & 1, b);
     keys_kernel<<<gb, 256, 0, s>>>(N, b, xyz, offset, st.gp, parity & 1, st.key_s, st.key_l, st.iota, st.wc);
     size_t tb = st.cub_bytes;
-    cub::DeviceRadixSort::SortPairs(st.cub_tmp, tb, st.key_s, st.skey_s, st.iota, st.order_s, N, 0, 32, s);
-    tb = st.cub_bytes;
-    cub::DeviceRadixSort::SortPairs(st.cub_tmp, tb, st.key_l, st.skey_l, st.iota, st.order_l, N, 0, 32, s);
+    cudaError_t ce;
+#define STB200_CUB(call)                                                                                         \
+    do {                                                                                                         \
+        tb = st.cub_bytes;                                                                                       \
+        if ((ce = (call)) != cudaSuccess) {                                                                      \
+            set_error("pair builder: %s failed: %s", #call, cudaGetErrorString(ce));                             \
+            return STB200_ERR_CUDA;                                                                              \
+        }                                                                                                        \
+    } while (0)
+    STB200_CUB(cub::DeviceRadixSort::SortPairs(st.cub_tmp, tb, st.key_s, st.skey_s, st.iota, st.order_s, N, 0, 32, s));
+    STB200_CUB(cub::DeviceRadixSort::SortPairs(st.cub_tmp, tb, st.key_l, st.skey_l, st.iota, st.order_l, N, 0, 32, s));
     flags_kernel<<<gb, 256, 0, s>>>(N, st.skey_s, st.skey_l, st.order_l, st.ds_mask, st.flag_s, st.flag_l, st.sflag);
-    tb = st.cub_bytes;
-    cub::DeviceScan::InclusiveSum(st.cub_tmp, tb, st.flag_s, st.rank_s, N + 1, s);
-    tb = st.cub_bytes;
-    cub::DeviceScan::InclusiveSum(st.cub_tmp, tb, st.flag_l, st.rank_l, N + 1, s);
-    tb = st.cub_bytes;
-    cub::DeviceScan::ExclusiveSum(st.cub_tmp, tb, st.sflag, st.spos, N + 1, s);
+    STB200_CUB(cub::DeviceScan::InclusiveSum(st.cub_tmp, tb, st.flag_s, st.rank_s, N + 1, s));
+    STB200_CUB(cub::DeviceScan::InclusiveSum(st.cub_tmp, tb, st.flag_l, st.rank_l, N + 1, s));
+    STB200_CUB(cub::DeviceScan::ExclusiveSum(st.cub_tmp, tb, st.sflag, st.spos, N + 1, s));
     scatter_windows_kernel<<<gb, 256, 0, s>>>(N, st.order_s, st.order_l, st.flag_s, st.flag_l, st.rank_s, st.rank_l,
                                               st.sflag, st.spos, st.wstart_s, st.wstart_l, st.win_s, st.win_l, st.samp);
     count_pairs_kernel<<<blocks_for((long long)N * kWarp), 256, 0, s>>>(N, st.win_s, st.win_l, st.wstart_s, st.wstart_l,
                                                                        st.spos, st.samp, st.wc, st.counts, st.gp,
                                                                        has_sparse);
-    tb = st.cub_bytes;
-    cub::DeviceScan::ExclusiveSum(st.cub_tmp, tb, st.counts, index0_offsets, N + 1, s);
+    STB200_CUB(cub::DeviceScan::ExclusiveSum(st.cub_tmp, tb, st.counts, index0_offsets, N + 1, s));
+#undef STB200_CUB
     finish_count_kernel<<<1, 32, 0, s>>>(N, index0_offsets, st.rank_s, st.gp, totals);
     return check_launch("stratified_pairs_count");
 }
@@ -684,9 +701,11 @@ int stb200_stratified_pairs_fill(int N, const float *xyz, float window_size_x2, 
             N, xyz, index0_offsets, st.win_s, st.win_l, st.wstart_s, st.wstart_l, st.order_s, st.spos, st.samp, st.wc,
             has_sparse, window_size_x2, quant_size, index_1, rel_idx, index_0);
     }
-    if (row_order) cudaMemcpyAsync(row_order, st.order_s, (size_t)N * sizeof(int), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
-    if (win_offsets && n_win > 0)
-        cudaMemcpyAsync(win_offsets, st.wstart_s, (size_t)(n_win + 1) * sizeof(int), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    cudaError_t ce = cudaSuccess;
+    if (row_order) ce = cudaMemcpyAsync(row_order, st.order_s, (size_t)N * sizeof(int), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    if (ce == cudaSuccess && win_offsets && n_win > 0)
+        ce = cudaMemcpyAsync(win_offsets, st.wstart_s, (size_t)(n_win + 1) * sizeof(int), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    STB200_REQUIRE(ce == cudaSuccess, STB200_ERR_CUDA, "pair builder: copy of the window order failed: %s", cudaGetErrorString(ce));
     return check_launch("stratified_pairs_fill");
 }
 
@@ -721,6 +740,13 @@ int stb200_rel_pos_index_swin(int N, const float *xyz, const int *index0_offsets
     return check_launch("rel_pos_index_swin");
 }
 
+
+int stb200_set_torch_semantics(int cuda) {
+    const int v = cuda ? 1 : 0;
+    const cudaError_t e = cudaMemcpyToSymbol(c_rel_cuda_division, &v, sizeof(int));
+    STB200_REQUIRE(e == cudaSuccess, STB200_ERR_CUDA, "set_torch_semantics: %s", cudaGetErrorString(e));
+    return STB200_OK;
+}
 
 // ---- fused work plan (include/stb200.h) ------------------------------------------------------------------------------
 size_t stb200_fused_plan_scratch_bytes(int N) {

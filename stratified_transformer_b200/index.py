@@ -23,6 +23,14 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def set_torch_semantics(device: str = "cuda") -> None:
+    """Which torch device's arithmetic the Stratified rel-pos index reproduces bit for bit: "cuda" (default; the reference as it
+    runs: `x / 100000` is a reciprocal multiply on CUDA tensors) or "cpu" (IEEE division; for fixtures made with CPU torch)."""
+    if device not in ("cuda", "cpu"):
+        raise ValueError("device must be 'cuda' or 'cpu'")
+    _cabi.call("stb200_set_torch_semantics", 1 if device == "cuda" else 0)
+
+
 FUSED_BLOCKS = dict(BQ=64, BK=64, BQS=48, BKS=32)   # block shapes the fused kernels are built for (dense square, sparse 48x32)
 _PLAN_MAXORD = 8
 
@@ -208,6 +216,9 @@ class PairIndex:
 
     def c_struct(self, L: int, backward: bool = False) -> "_cabi.IndexStruct":
         """`stb200_index` for the fused entry points; packs the rel-pos bins on first use (per table length)."""
+        if self.index_1 is None or self.rel_idx is None:
+            raise ValueError("PairIndex: the per-op entry points need the CSR pair list with its rel-pos index (built with csr=True "
+                             "and a quant_size, or rel_idx filled by WindowAttention.forward); this index only carries the fused plan")
         ent = self._packed.get(L)
         if ent is None:
             ent = [self._pack(L, None), None]

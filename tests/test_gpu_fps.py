@@ -85,3 +85,16 @@ def test_fps_streaming_fallback_for_very_large_scene():
     new_offset = io.fps_new_offset(offset, 64)
     want = fps_oracle.furthestsampling(xyz, offset, new_offset)
     assert np.array_equal(ours(xyz, offset, new_offset), want)
+
+
+@pytest.mark.parametrize("b,n_big", [(20, 30000), (38, 9000)])
+def test_fps_large_batches_fall_back_to_streaming(b, n_big):
+    """Batches whose cluster configuration exceeds the register kernel's budget (b = 20 scenes with a 30k-point one: cluster 2
+    x 512 threads x 30 points per thread; b >= 38: one CTA per scene, 1024 threads, more than 8 points per thread) used to
+    fail with STB200_ERR_ARG; they must take the streaming kernel and stay exact."""
+    sizes = [n_big] + [600 + 37 * i for i in range(b - 1)]
+    xyz = np.concatenate([scene(n, 100 + i) for i, n in enumerate(sizes)])
+    offset = np.cumsum(sizes).astype(np.int32)
+    new_offset = io.fps_new_offset(offset, 64)
+    want = fps_oracle.furthestsampling(xyz, offset, new_offset)
+    assert np.array_equal(ours(xyz, offset, new_offset), want)

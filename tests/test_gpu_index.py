@@ -31,7 +31,12 @@ def test_pairs_match_reference_golden(golden_dir, name):
     ds_idx = pointops.furthestsampling(torch.from_numpy(xyz).cuda(), off_d, new_offset).cpu().numpy()
     assert np.array_equal(ds_idx, g["downsample_idx"])
     for parity in (0, 1):
-        r = build(xyz, offset, w, quant, ds_idx, parity, want_index_0=True)
+        index.set_torch_semantics("cpu")        # the goldens come from CPU torch (no GPU where they were generated)
+        try:
+            r = build(xyz, offset, w, quant, ds_idx, parity, want_index_0=True)
+            torch.cuda.synchronize()
+        finally:
+            index.set_torch_semantics("cuda")
         offs = r.index_0_offsets.cpu().numpy()
         assert np.array_equal(offs, g[f"p{parity}_offsets"])
         assert r.n_max == int(g[f"p{parity}_n_max"]) and r.M == offs[-1]
@@ -43,7 +48,7 @@ def test_pairs_match_reference_golden(golden_dir, name):
         assert np.array_equal(i1, o["index_1"])
         assert np.array_equal(r.index_0.cpu().numpy(), o["index_0"])
         rel = r.rel_idx.cpu().numpy()
-        assert np.array_equal(rel, io.rel_pos_index_stratified(xyz, o["index_0"], o["index_1"], w, quant))
+        assert np.array_equal(rel, io.rel_pos_index_stratified(xyz, o["index_0"], o["index_1"], w, quant, device="cpu"))
         # and the rel-pos index agrees with the reference's torch evaluation once both are canonicalised
         seg = np.repeat(np.arange(offs.shape[0] - 1), np.diff(offs))
         order = np.lexsort((i1, seg))
@@ -275,3 +280,24 @@ def test_length_order_is_a_stable_sort_by_pair_count(golden_dir):
     t_off = pi.tcsr.t_offsets.cpu().numpy().astype(np.int64)
     t_lens = t_off[1:] - t_off[:-1]
     assert np.array_equal(k_order.cpu().numpy(), base[np.argsort(t_lens[base], kind="stable")])
+
+
+def test_rel_pos_index_matches_the_reference_statements_on_cuda():
+    """The reference as it really runs: its three torch statements (model/stratified_transformer.py:186-188) evaluated on
+    CUDA tensors on this box, against the builder's rel-pos index (default "cuda" arithmetic) — exact, on 1.5 M pairs; and
+    the numpy oracle in the same mode.  CPU torch differs from both in a few pairs (scalar division = reciprocal multiply on
+    CUDA), which is why the CPU-generated goldens are compared in the "cpu" mode."""
+    from stratified_transformer_b200.synthetic import make_batch
+    xyz, _, offset = make_batch(2, 20000, seed0=3, n_raw=600_000)
+    for w, quant in ((0.16, 0.01), (0.32, 0.02), (0.2, 0.01)):
+        ds_idx = fps_oracle.furthestsampling(xyz, offset, io.fps_new_offset(offset, 8))
+        r = build(xyz, offset, w, quant, ds_idx, 1, want_index_0=True)
+        xd = torch.from_numpy(xyz).cuda()
+        i0, i1 = r.index_0.long(), r.index_1.long()
+        rel = xd[i0] - xd[i1]
+        rel = torch.round(rel * 100000) / 100000
+        want = ((rel + 2 * w - 0.0001) // quant).int()
+        assert torch.equal(r.rel_idx, want)
+        assert np.array_equal(want.cpu().numpy(), io.rel_pos_index_stratified(xyz, i0.cpu().numpy(), i1.cpu().numpy(), w, quant, device="cuda"))
+        cpu = ((torch.round((xd.cpu()[i0.cpu()] - xd.cpu()[i1.cpu()]) * 100000) / 100000 + 2 * w - 0.0001) // quant).int()
+        assert int((cpu != want.cpu()).sum()) < 1e-3 * want.numel()

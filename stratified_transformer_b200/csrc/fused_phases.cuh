@@ -82,6 +82,7 @@ struct PassParams {
     float *gq, *gk, *gv;            // [N,h,16]
     float *gtq, *gtk, *gtv;         // [L,h,16,3], accumulated into
     int dbg;                        // development switches (STB200_FUSED_DBG), 0 in production
+    long long *prof;                // optional [64] per-phase cycle totals of CTA 0 (stb200_fused_phase_profile), else NULL
 };
 
 struct Layout {   // offsets in floats into the CTA's shared memory

@@ -34,6 +34,22 @@
 #define TC_PER_THREAD_USE(type, name) type *name = name##_all[fw_tid_]
 #endif
 
+// per-phase clock stamps of one CTA (development: tools/fused_phase_prof.py): cycles since the previous stamp are added to slot k
+#if defined(__CUDACC__) && !defined(FW_HOST_EMU)
+#define TC_STAMP(k)                                                                  \
+    do {                                                                             \
+        if (prof_on) {                                                               \
+            const long long now_ = clock64();                                        \
+            if (threadIdx.x == 0) atomicAdd((unsigned long long *)(P.prof + (k)), (unsigned long long)(now_ - last_stamp)); \
+            last_stamp = now_;                                                       \
+        }                                                                            \
+    } while (0)
+#define TC_STAMP_DECL const bool prof_on = P.prof != nullptr && cta == 0 && head == 0; long long last_stamp = prof_on ? clock64() : 0
+#else
+#define TC_STAMP(k) do { } while (0)
+#define TC_STAMP_DECL do { } while (0)
+#endif
+
 namespace stb200 {
 namespace fwtc {
 
@@ -336,6 +352,7 @@ FW_FN void forward_cta_tc(const PassParams &P, int head, int cta, int n_cta, uns
     float *red = reinterpret_cast<float *>(smb + y.red), *mrow = reinterpret_cast<float *>(smb + y.mrow), *lrow = reinterpret_cast<float *>(smb + y.lrow);
     const int h = P.h, lo = P.bin_lo, RB = P.RB, Rpad = P.Rpad;
     const int c_qt = C_WORK, c_kt = C_WORK + Rpad, c_s = C_WORK + 2 * Rpad;
+    TC_STAMP_DECL;
 
     TC_PHASE_BEGIN
         const int tid = FW_TID;
@@ -352,6 +369,7 @@ FW_FN void forward_cta_tc(const PassParams &P, int head, int cta, int n_cta, uns
         TC_PHASE_BEGIN   // ---- 0
             describe_item_tc<BQ, BK>(P, it, rowinfo, keyid, FW_TID);
         TC_PHASE_END
+        TC_STAMP(0);
 
         TC_PHASE_BEGIN   // ---- 1: stage q, k as chunked hi / lo rows (64 rows each, padding rows zero), v plain, the rel tile
             const int tid = FW_TID;
@@ -372,6 +390,7 @@ FW_FN void forward_cta_tc(const PassParams &P, int head, int cta, int n_cta, uns
             }
             tc_publish_smem();
         TC_PHASE_END
+        TC_STAMP(1);
 
         TC_PHASE_BEGIN   // ---- 2: products and the q.k tile on the tensor cores
             const int tid = FW_TID;
@@ -383,7 +402,9 @@ FW_FN void forward_cta_tc(const PassParams &P, int head, int cta, int n_cta, uns
                 tc_commit(ctx);
             }
         TC_PHASE_END
+        TC_STAMP(2);
         tc_wait(ctx);
+        TC_STAMP(3);
 
         TC_PHASE_BEGIN   // ---- 3: accumulators -> shared memory
             const int tid = FW_TID;
@@ -392,6 +413,7 @@ FW_FN void forward_cta_tc(const PassParams &P, int head, int cta, int n_cta, uns
             tmem_to_smem_m64(ctx, tid, c_s, nk4, nq4, S, y.PS, false);
             tc_tmem_reads_done();
         TC_PHASE_END
+        TC_STAMP(4);
 
         TC_PHASE_BEGIN   // ---- 4: logits of the valid pairs, -inf elsewhere; partial row maxima (8 stripes per row)
             const int tid = FW_TID;
@@ -415,6 +437,7 @@ FW_FN void forward_cta_tc(const PassParams &P, int head, int cta, int n_cta, uns
                 red[i * 8 + st] = mx;
             }
         TC_PHASE_END
+        TC_STAMP(5);
 
         TC_PHASE_BEGIN   // ---- 5: row maxima; clear the histogram (the query products are dead now)
             const int tid = FW_TID;
@@ -426,6 +449,7 @@ FW_FN void forward_cta_tc(const PassParams &P, int head, int cta, int n_cta, uns
             }
             for (int e = tid; e < Rpad * PH / 4; e += NTC) reinterpret_cast<float4 *>(PhT)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
         TC_PHASE_END
+        TC_STAMP(6);
 
         TC_PHASE_BEGIN   // ---- 6: p = exp(s - max) in place, partial row sums
             const int tid = FW_TID;
@@ -442,6 +466,7 @@ FW_FN void forward_cta_tc(const PassParams &P, int head, int cta, int n_cta, uns
                 red[i * 8 + st] = sum;
             }
         TC_PHASE_END
+        TC_STAMP(7);
 
         TC_PHASE_BEGIN   // ---- 7: histogram Ph[bin][i] += p_ij (one thread per (row, axis)); row sums
             const int tid = FW_TID;
@@ -462,6 +487,7 @@ FW_FN void forward_cta_tc(const PassParams &P, int head, int cta, int n_cta, uns
                 }
             }
         TC_PHASE_END
+        TC_STAMP(8);
 
         TC_PHASE_BEGIN   // ---- 8: out tile = P V + Ph T_v in KSF K-slices
             const int tid = FW_TID;
@@ -501,6 +527,7 @@ FW_FN void forward_cta_tc(const PassParams &P, int head, int cta, int n_cta, uns
                     red[i * 8 + 1] = P.l[rowh];
                 }
         TC_PHASE_END
+        TC_STAMP(9);
 
         TC_PHASE_BEGIN   // ---- 9: merge with the partial of an earlier pass, normalise on the final pass, store
             const int tid = FW_TID;
@@ -537,6 +564,7 @@ FW_FN void forward_cta_tc(const PassParams &P, int head, int cta, int n_cta, uns
                 }
             }
         TC_PHASE_END
+        TC_STAMP(10);
     }
 }
 
@@ -562,6 +590,7 @@ FW_FN void backward_cta_tc(const PassParams &P, int head, int cta, int n_cta, un
     TC_PER_THREAD(float, lo_sk, HK_CH * 4);
     bool q_acc_live = false, k_acc_live = false;   // table-gradient accumulators already hold a product (else the first MMA overwrites)
     const uint32_t hq_bytes = (uint32_t)(y.HR / 8) * y.ro_hq, hk_bytes = (uint32_t)(y.HR / 8) * y.ro_hk;
+    TC_STAMP_DECL;
 
     TC_PHASE_BEGIN
         const int tid = FW_TID;
@@ -578,6 +607,7 @@ FW_FN void backward_cta_tc(const PassParams &P, int head, int cta, int n_cta, un
         TC_PHASE_BEGIN   // ---- 0
             describe_item_tc<BQ, BK>(P, it, rowinfo, keyid, FW_TID);
         TC_PHASE_END
+        TC_STAMP(0);
 
         TC_PHASE_BEGIN   // ---- 1: stage q, g, k (R-form and T-form), v (R-form), all hi / lo; g.out partials, LSE, rel tile
             const int tid = FW_TID;
@@ -618,6 +648,7 @@ FW_FN void backward_cta_tc(const PassParams &P, int head, int cta, int n_cta, un
             }
             tc_publish_smem();
         TC_PHASE_END
+        TC_STAMP(1);
 
         TC_PHASE_BEGIN   // ---- 2: QT product and both tiles
             const int tid = FW_TID;
@@ -630,7 +661,9 @@ FW_FN void backward_cta_tc(const PassParams &P, int head, int cta, int n_cta, un
             }
             for (int i = tid; i < BQ; i += NTC) drow[i] = (red[i * 8] + red[i * 8 + 1]) + (red[i * 8 + 2] + red[i * 8 + 3]);
         TC_PHASE_END
+        TC_STAMP(2);
         tc_wait(ctx);
+        TC_STAMP(3);
 
         TC_PHASE_BEGIN   // ---- 3
             const int tid = FW_TID;
@@ -639,6 +672,7 @@ FW_FN void backward_cta_tc(const PassParams &P, int head, int cta, int n_cta, un
             tmem_to_smem_m64(ctx, tid, c_gv, nk4, nq4, GS, y.PS, false);
             tc_tmem_reads_done();
         TC_PHASE_END
+        TC_STAMP(4);
 
         TC_PHASE_BEGIN   // ---- 4: KT product
             if (FW_TID == 0) {
@@ -647,12 +681,15 @@ FW_FN void backward_cta_tc(const PassParams &P, int head, int cta, int n_cta, un
                 tc_commit(ctx);
             }
         TC_PHASE_END
+        TC_STAMP(5);
         tc_wait(ctx);
+        TC_STAMP(6);
 
         TC_PHASE_BEGIN   // ---- 5
             tmem_to_smem_m64(ctx, FW_TID, c_prod, Rpad, nk4, B2f, y.RP, true);
             tc_tmem_reads_done();
         TC_PHASE_END
+        TC_STAMP(7);
 
         TC_PHASE_BEGIN   // ---- 6: GT product in flight while p = exp(s - LSE) is computed
             const int tid = FW_TID;
@@ -679,12 +716,15 @@ FW_FN void backward_cta_tc(const PassParams &P, int head, int cta, int n_cta, un
                 }
             }
         TC_PHASE_END
+        TC_STAMP(8);
         tc_wait(ctx);
+        TC_STAMP(9);
 
         TC_PHASE_BEGIN   // ---- 7
             tmem_to_smem_m64(ctx, FW_TID, c_prod, Rpad, nq4, B1f, y.RP, true);
             tc_tmem_reads_done();
         TC_PHASE_END
+        TC_STAMP(10);
 
         TC_PHASE_BEGIN   // ---- 8: gs = p (g.v + GT look-ups - g.out)
             const int tid = FW_TID;
@@ -704,6 +744,7 @@ FW_FN void backward_cta_tc(const PassParams &P, int head, int cta, int n_cta, un
                 }
             }
         TC_PHASE_END
+        TC_STAMP(11);
 
         TC_PHASE_BEGIN   // ---- 9: clear the three histograms: Sq -> B1, Ph -> B2 ([bin][query row]), Sk -> B3 ([bin][key row], over the dead R-form rows)
             const int tid = FW_TID;
@@ -714,6 +755,7 @@ FW_FN void backward_cta_tc(const PassParams &P, int head, int cta, int n_cta, un
             }
             for (uint32_t e = tid; e < hk_bytes / 16; e += NTC) reinterpret_cast<float4 *>(smb + y.B3)[e] = z;
         TC_PHASE_END
+        TC_STAMP(12);
 
         TC_PHASE_BEGIN   // ---- 10: build them (thread per (query row, axis), thread per (key row, axis))
             const int tid = FW_TID;
@@ -741,6 +783,7 @@ FW_FN void backward_cta_tc(const PassParams &P, int head, int cta, int n_cta, un
                 }
             }
         TC_PHASE_END
+        TC_STAMP(13);
 
         TC_PHASE_BEGIN   // ---- 11: gq, gk, gv tiles on the FMA pipe (two K-halves each); the rel tile is dead, its space takes the partials
             const int tid = FW_TID;
@@ -807,6 +850,7 @@ FW_FN void backward_cta_tc(const PassParams &P, int head, int cta, int n_cta, un
                 for (int r = 0; r < 4; ++r) *reinterpret_cast<float4 *>(dst + r * HD) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
             }
         TC_PHASE_END
+        TC_STAMP(14);
 
         TC_PHASE_BEGIN   // ---- 12: split the histograms in place (hi stays, lo in registers); write the gradient rows
             const int tid = FW_TID;
@@ -868,6 +912,7 @@ FW_FN void backward_cta_tc(const PassParams &P, int head, int cta, int n_cta, un
                 }
             }
         TC_PHASE_END
+        TC_STAMP(15);
 
         // ---- 13 / 14: table gradients on the tensor cores: gT_q += Sq^T Q, gT_v += Ph^T G, gT_k += Sk^T K.
         // A = histogram [bin][row] (M = 128 bins per MMA, K = rows), B = T-form rows [16][row] (N = 16).
@@ -895,6 +940,7 @@ FW_FN void backward_cta_tc(const PassParams &P, int head, int cta, int n_cta, un
                     tc_publish_smem();
                 }
             TC_PHASE_END
+            TC_STAMP(16);
             TC_PHASE_BEGIN
                 if (FW_TID == 0) {
                     tc_begin_issue();
@@ -915,7 +961,9 @@ FW_FN void backward_cta_tc(const PassParams &P, int head, int cta, int n_cta, un
                     tc_commit(ctx);
                 }
             TC_PHASE_END
+            TC_STAMP(17);
             tc_wait(ctx);
+            TC_STAMP(18);
         }
         q_acc_live = q_acc_live || nq8 > 0;
         k_acc_live = k_acc_live || nk8 > 0;
@@ -946,6 +994,7 @@ FW_FN void backward_cta_tc(const PassParams &P, int head, int cta, int n_cta, un
         }
         tc_tmem_reads_done();
     TC_PHASE_END
+    TC_STAMP(19);
 }
 
 }  // namespace fwtc

@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(fw::NT, 1) fused_window_kernel(const PassParam
 }
 
 constexpr size_t kMaxSmem = 232448;   // 227 KB opt-in limit per CTA on sm_100a
+static long long *g_phase_prof = nullptr;   // development aid, see stb200_fused_phase_profile
 
 // tensor-core version (fused_tc.cuh): 512 threads, 512 TMEM columns per CTA, one mbarrier for MMA completion
 template <int BQ, int BK, int HRT, bool BWD>
@@ -102,6 +103,7 @@ static int dispatch_pass(const stb200_fused_pass &ps, PassParams &P, const char 
     P.pos_win = ps.pos_win; P.wstart = ps.wstart; P.tile_base = ps.tile_base;
     P.bin_lo = ps.bin_lo; P.RB = ps.RB;
     { const char *e = std::getenv("STB200_FUSED_DBG"); P.dbg = e ? std::atoi(e) : 0; }
+    P.prof = g_phase_prof;
     P.Rpad = (3 * ps.RB + 15) / 16 * 16;
     STB200_REQUIRE(ps.RB > 0 && P.Rpad <= 256, STB200_ERR_ARG, "fused window attention stages at most 85 bins per axis (got %d)", ps.RB);
     if (use_tc()) {   // tensor-core kernels where their shared-memory plan fits (S3DIS table length: both passes)
@@ -123,6 +125,10 @@ static int dispatch_pass(const stb200_fused_pass &ps, PassParams &P, const char 
 using namespace stb200;
 
 extern "C" {
+
+/* development aid: device buffer of 64 int64 that CTA 0 / head 0 of every later tcgen05 fused launch adds its per-phase cycle
+ * counts to (NULL switches it off); tools/fused_phase_prof.py */
+void stb200_fused_phase_profile(long long *device_buffer) { g_phase_prof = device_buffer; }
 
 int stb200_fused_attention_forward(const stb200_fused_pass *passes, int n_passes, int N, int h, int L, const float *q, const float *k,
                                    const float *v, const float *table_q, const float *table_k, const float *table_v, float *out,

@@ -293,7 +293,10 @@ def build_inputs(a, rank, dev):
     """Scenes, point hierarchy (precomputed with the library's own FPS) and per-layer operands, on the host and device."""
     from stratified_transformer_b200 import pointops
     from stratified_transformer_b200.synthetic import make_batch
-    xyz0, rgb, offset0 = make_batch(a.scenes, a.points, seed0=100 * rank)
+    # STB200_BENCH_SAME_SCENES=1 (diagnostic): every rank draws the SAME scenes, which removes the data-dependent
+    # straggler from a multi-rank run and leaves only the exchange + host effects
+    seed0 = 0 if os.environ.get("STB200_BENCH_SAME_SCENES") else 100 * rank
+    xyz0, rgb, offset0 = make_batch(a.scenes, a.points, seed0=seed0)
     levels = []
     xyz_d = torch.from_numpy(xyz0).to(dev)
     off_d = torch.from_numpy(offset0).to(dev)
@@ -638,7 +641,7 @@ def main():
             grads = device_step(levels, [], geo, not a.fused)
         if pf is not None:
             pf.complete()
-        if dist is not None:   # training only: data-parallel gradient all-reduce of the attention parameters (parallel.py)
+        if dist is not None and not os.environ.get("STB200_BENCH_NO_ALLREDUCE"):   # training only: data-parallel gradient all-reduce of the attention parameters (parallel.py)
             from stratified_transformer_b200 import parallel
             parallel.allreduce_gradients([t for trip in grads for t in trip], average=True)
         return grads

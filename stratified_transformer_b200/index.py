@@ -467,24 +467,38 @@ class GeometryPrefetcher:
         self.cfgs = layer_cfgs
         self.fused, self.csr = fused, csr
         # stream priority of the geometry work relative to the attention stream (0 = default, -1 = higher)
-        self.side = torch.cuda.Stream(device=device, priority=int(os.environ.get("STB200_SIDE_PRIORITY", "0")))
+        prio = int(os.environ.get("STB200_SIDE_PRIORITY", "0"))
+        # One side stream per layer (STB200_GEOMETRY_STREAMS=1: a single one, the round-1 behaviour): the layers' point sets
+        # are independent, and each layer's FPS is a sequential loop of ~n/ds iterations that occupies a few SMs, so the
+        # four loops run side by side instead of back to back (critical path = layer 0's FPS + its pair lists).
+        n_streams = max(1, min(len(layer_cfgs), int(os.environ.get("STB200_GEOMETRY_STREAMS", str(len(layer_cfgs))))))
+        self.sides = [torch.cuda.Stream(device=device, priority=prio) for _ in range(n_streams)]
+        self.side = self.sides[0]
         self.pending = None
         self.done = None
 
+    def _stream_of(self, layer):
+        return self.sides[layer % len(self.sides)]
+
     def submit(self, xyzs, offsets, offsets_host):
         main = torch.cuda.current_stream()
-        self.side.wait_stream(main)           # inputs produced on the main stream are visible
-        with torch.cuda.stream(self.side):
-            self.pending = [PendingLayerIndex(x, o, w, q, ds, oh, L=L, fused=self.fused, csr=self.csr)
-                            for x, o, oh, (w, q, ds, L) in zip(xyzs, offsets, offsets_host, self.cfgs)]
-        for x in xyzs:
-            x.record_stream(self.side)
+        self.pending = []
+        for i, (x, o, oh, (w, q, ds, L)) in enumerate(zip(xyzs, offsets, offsets_host, self.cfgs)):
+            side = self._stream_of(i)
+            side.wait_stream(main)            # inputs produced on the main stream are visible,
+            if side is not self.side:
+                side.wait_stream(self.side)   # and so are uploads the caller enqueued on `self.side`
+            with torch.cuda.stream(side):
+                self.pending.append(PendingLayerIndex(x, o, w, q, ds, oh, L=L, fused=self.fused, csr=self.csr))
+            x.record_stream(side)
 
     def complete(self):
         if self.pending is None:
             return
-        with torch.cuda.stream(self.side):
-            self.done = [p.finish() for p in self.pending]
+        self.done = []
+        for i, p in enumerate(self.pending):
+            with torch.cuda.stream(self._stream_of(i)):
+                self.done.append(p.finish())
         self.pending = None
 
     def take(self):

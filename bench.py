@@ -322,7 +322,7 @@ def build_inputs(a, rank, dev):
     return levels, torch.from_numpy(rgb)
 
 
-def device_step(levels, grads_out, geo=None, no_fused=True, backward=True):
+def device_step(levels, grads_out, geo=None, no_fused=True, backward=True, on_level_done=None):
     """One pass of the hot path with device-resident operands through the extension-level API (fused entry points:
     logits = q.k + rel-pos bias in one pass, segment softmax, aggregation; and their single-pass gradients)."""
     import ctypes
@@ -375,10 +375,12 @@ def device_step(levels, grads_out, geo=None, no_fused=True, backward=True):
                        k.data_ptr(), tq.data_ptr(), tk.data_ptr(), gq.data_ptr(), gk.data_ptr(), gtq.data_ptr(),
                        gtk.data_ptr(), ws.data_ptr(), wsb, stream)
             grads_out.append((gtq, gtk, gtv))
+        if on_level_done is not None:   # this layer's parameter gradients are final: their exchange can start now
+            on_level_done(grads_out[-cfg["depth"]:])
     return grads_out
 
 
-def device_step_fused(levels, grads_out, geo, backward=True):
+def device_step_fused(levels, grads_out, geo, backward=True, on_level_done=None):
     """One pass of the hot path on the window-centric fused kernels: per block one forward (dense pass + sparse pass) that
     keeps only the output and the row log-sum-exp, and one backward producing the six gradients.  No [M,h] tensor."""
     from stratified_transformer_b200 import _cabi
@@ -632,18 +634,28 @@ def main():
         if pf is not None:
             geo = pf.take()
             pf.submit(xyzs_d, offs_d, offs_h)
+        # training only: data-parallel all-reduce of the attention parameters' gradients (parallel.py), started per layer as
+        # soon as the layer's last block has been differentiated and finished at the end of the step
+        pending = []
+        on_level = None
+        if dist is not None and not os.environ.get("STB200_BENCH_NO_ALLREDUCE"):
+            from stratified_transformer_b200 import parallel
+
+            def on_level(level_grads):
+                fin = parallel.allreduce_gradients([t for trip in level_grads for t in trip], average=True, async_op=True)
+                if fin is not None:
+                    pending.append(fin)
         if use_fused:
             if geo is None:
                 geo = [st_index.build_layer_index(lv["xyz"], lv["offset"], lv["cfg"]["window"], lv["cfg"]["quant"], DS_SCALE,
                                                   fused=True, csr=False) for lv in levels]
-            grads = device_step_fused(levels, [], geo)
+            grads = device_step_fused(levels, [], geo, on_level_done=on_level)
         else:
-            grads = device_step(levels, [], geo, not a.fused)
+            grads = device_step(levels, [], geo, not a.fused, on_level_done=on_level)
         if pf is not None:
             pf.complete()
-        if dist is not None and not os.environ.get("STB200_BENCH_NO_ALLREDUCE"):   # training only: data-parallel gradient all-reduce of the attention parameters (parallel.py)
-            from stratified_transformer_b200 import parallel
-            parallel.allreduce_gradients([t for trip in grads for t in trip], average=True)
+        for fin in pending:
+            fin()
         return grads
 
     for _ in range(max(a.warmup, 3)):
@@ -734,6 +746,14 @@ def main():
         for _ in range(2):
             e2e_step()
         barrier()
+        if os.environ.get("STB200_BENCH_E2E_TRACE") and rank == 0:   # development aid: kernel table of two e2e steps (untimed)
+            from torch.profiler import profile, ProfilerActivity
+            with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as tp:
+                for _ in range(2):
+                    e2e_step()
+                torch.cuda.synchronize()
+            with open(os.environ["STB200_BENCH_E2E_TRACE"], "w") as f:
+                f.write(tp.key_averages().table(sort_by="cuda_time_total", row_limit=80, max_name_column_width=90))
         n_e2e = max(3, min(a.steps, 10))
         t0 = time.perf_counter()
         for _ in range(n_e2e):

@@ -44,7 +44,7 @@ const char *stb200_last_error(void);
 /* number of kernels this library launched since load (bench.py's "gpu_launches") */
 long long stb200_launch_count(void);
 /* ABI version: 100 = first release, 101 = stb200_index has len_order / t_len_order (append-only struct growth),
- * 102 = fused work plan + fused window attention entry points */
+ * 102 = fused work plan + fused window attention entry points; 103 = stb200_qkv_split / _merge */
 int stb200_version(void);
 /* Optional per-kernel profiler: when enabled every launch is bracketed by CUDA events on its stream.
  * stb200_profile_dump writes a JSON object {"kernel name": {"launches", "ms", "bytes"}} (bytes = algorithmic bytes
@@ -318,6 +318,20 @@ int stb200_fused_attention_backward(const stb200_fused_pass *passes, int n_passe
  * mode 2: A [M,K] (K-major), B [K,N] (MN-major) -> A B.  M in {64, 128}, N, K multiples of 8.  out [128, N] receives TMEM
  * lanes 0..127 of the accumulator; *status becomes 1 when the MMA never signalled completion. */
 int stb200_tc_selftest(int mode, int M, int N, int K, const float *A, const float *B, float *out, int *status, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * The elementwise passes of WindowAttention.forward around the pair ops (model/stratified_transformer.py:172-175 and the
+ * `.float()` casts at lines 193-216), one kernel each way.
+ * stb200_qkv_split: qkv [N, 3C] (dtype 0 = fp32, 1 = bf16, 2 = fp16; the output of the projection GEMM WITHOUT its bias)
+ *     -> q, k, v fp32 [N, C] contiguous (= [N, h, C/h]), bias [3C] added (NULL: none).  The caller folds `scale` into the q rows
+ *     of the weight and bias.
+ * stb200_qkv_merge: grad_q, grad_k, grad_v fp32 [N, C] -> grad_qkv [N, 3C] in `dtype`, and, when bias_partial != NULL,
+ *     per-CTA column sums bias_partial [stb200_qkv_partial_rows(N, C), 3C] whose sum over rows is the bias gradient
+ *     (deterministic: no atomics).  C must be a multiple of 8, 3C <= 2048. */
+int stb200_qkv_partial_rows(int N, int C);
+int stb200_qkv_split(int N, int C, int dtype, const void *qkv, const float *bias, float *q, float *k, float *v, void *stream);
+int stb200_qkv_merge(int N, int C, int dtype, const float *grad_q, const float *grad_k, const float *grad_v, void *grad_qkv,
+                     float *bias_partial, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * k nearest neighbours per scene — replaces knnquery_cuda_launcher

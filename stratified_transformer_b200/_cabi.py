@@ -77,6 +77,8 @@ _SIGNATURES = {
     "stb200_fused_attention_forward": [_FP, _c_int, _c_int, _c_int, _c_int] + [P] * 10,
     "stb200_fused_attention_backward": [_FP, _c_int, _c_int, _c_int, _c_int] + [P] * 16,
     "stb200_tc_selftest": [_c_int] * 4 + [P] * 5,
+    "stb200_qkv_split": [_c_int] * 3 + [P] * 6,
+    "stb200_qkv_merge": [_c_int] * 3 + [P] * 6,
     "stb200_set_torch_semantics": [_c_int],
     "stb200_rel_pos_index_swin": [_c_int, P, P, P, ctypes.c_float, ctypes.c_float, ctypes.c_float, _c_int, P, P, P, P],
 }
@@ -90,6 +92,7 @@ _RESTYPES = {
     "stb200_pair_builder_workspace_bytes": (_c_size_t, [_c_int]),
     "stb200_fused_max_keys": (_c_int, []),
     "stb200_fused_plan_scratch_bytes": (_c_size_t, [_c_int]),
+    "stb200_qkv_partial_rows": (_c_int, [_c_int, _c_int]),
     "stb200_profile_enable": (None, [_c_int]),
     "stb200_profile_dump": (_c_size_t, [ctypes.c_char_p, _c_size_t]),
 }
@@ -121,8 +124,8 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = restype
-    if lib.stb200_version() < 102:   # the IndexStruct mirror below needs the 101 layout (len_order / t_len_order)
-        raise Stb200Error(f"{LIB_PATH} is stale (ABI {lib.stb200_version()} < 102): rebuild it with `make -C stratified_transformer_b200/csrc`")
+    if lib.stb200_version() < 103:   # the IndexStruct mirror below needs the 101 layout (len_order / t_len_order)
+        raise Stb200Error(f"{LIB_PATH} is stale (ABI {lib.stb200_version()} < 103): rebuild it with `make -C stratified_transformer_b200/csrc`")
     _lib = lib
     return lib
 

@@ -1,0 +1,166 @@
+// The elementwise passes of WindowAttention.forward around the pair ops, fused into one kernel each way.
+//
+// Reference (/root/reference/model/stratified_transformer.py:172-175):
+//     qkv = self.qkv(feats).reshape(N, 3, h, C // h).permute(1, 0, 2, 3).contiguous();  query = query * self.scale
+// followed by `.float()` at every pointops call under AMP (lines 193-216).  As torch ops that is, per block, a bias add inside the
+// GEMM epilogue, an N x 3C permute copy, a multiply, three casts forward and three casts + a concatenation + a bias
+// reduction backward.  Here the projection GEMM runs without a bias and ONE kernel turns its [N, 3C] output (fp32, bf16 or
+// fp16) into the three contiguous fp32 [N, h, d] operands (bias added, scale already folded into the weights by the caller);
+// the backward kernel writes the [N, 3C] gradient in the GEMM's dtype and the bias gradient (column sums) in the same pass.
+//
+// HBM-bound streaming: 16 B loads / stores, grid = a multiple of the SM count, every byte touched once.
+#include "common.cuh"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+namespace stb200 {
+
+template <typename T> struct Vec8;   // 8 consecutive elements <-> 8 floats
+template <> struct Vec8<float> {
+    static __device__ __forceinline__ void load(const float *p, float (&x)[8]) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(p)), b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+    }
+    static __device__ __forceinline__ void store(float *p, const float (&x)[8]) {
+        reinterpret_cast<float4 *>(p)[0] = make_float4(x[0], x[1], x[2], x[3]);
+        reinterpret_cast<float4 *>(p)[1] = make_float4(x[4], x[5], x[6], x[7]);
+    }
+};
+template <> struct Vec8<__nv_bfloat16> {
+    static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float (&x)[8]) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4 *>(p));
+        const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); x[2 * i] = f.x; x[2 * i + 1] = f.y; }
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16 *p, const float (&x)[8]) {
+        uint4 u;
+        __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
+        *reinterpret_cast<uint4 *>(p) = u;
+    }
+};
+template <> struct Vec8<__half> {
+    static __device__ __forceinline__ void load(const __half *p, float (&x)[8]) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4 *>(p));
+        const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); x[2 * i] = f.x; x[2 * i + 1] = f.y; }
+    }
+    static __device__ __forceinline__ void store(__half *p, const float (&x)[8]) {
+        uint4 u;
+        __half2 *h = reinterpret_cast<__half2 *>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+        *reinterpret_cast<uint4 *>(p) = u;
+    }
+};
+
+constexpr int kQkvThreads = 256;
+
+// Work item = 8 consecutive columns of one row of the [N, 3C] matrix; G = 3C/8 items per row.  A thread keeps its column
+// group for the whole kernel (the item stride is a multiple of G), so the backward kernel can sum its columns in registers.
+template <typename T>
+__global__ void __launch_bounds__(kQkvThreads) qkv_split_kernel(int N, int C, const T *__restrict__ qkv, const float *__restrict__ bias,
+                                                                float *__restrict__ q, float *__restrict__ k, float *__restrict__ v,
+                                                                int rows_per_step) {
+    const int G = 3 * C / 8;
+    const int cg = threadIdx.x % G, lr = threadIdx.x / G;   // threads beyond rows_per_step * G idle (G need not divide 256)
+    if (lr >= rows_per_step) return;
+    const int col = cg * 8, part = col / C, pc = col - part * C;
+    float *dst = part == 0 ? q : (part == 1 ? k : v);
+    float b[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (bias) Vec8<float>::load(bias + col, b);
+    for (long long r = (long long)blockIdx.x * rows_per_step + lr; r < N; r += (long long)gridDim.x * rows_per_step) {
+        float x[8];
+        Vec8<T>::load(qkv + r * 3 * C + col, x);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] += b[i];
+        Vec8<float>::store(dst + r * C + pc, x);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kQkvThreads) qkv_merge_kernel(int N, int C, const float *__restrict__ gq, const float *__restrict__ gk,
+                                                                const float *__restrict__ gv, T *__restrict__ g_qkv,
+                                                                float *__restrict__ bias_partial, int rows_per_step) {
+    __shared__ float red[kQkvThreads * 8];
+    const int G = 3 * C / 8;
+    const int cg = threadIdx.x % G, lr = threadIdx.x / G;
+    const bool active = lr < rows_per_step;
+    const int col = cg * 8, part = col / C, pc = col - part * C;
+    const float *src = part == 0 ? gq : (part == 1 ? gk : gv);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (active) {
+        for (long long r = (long long)blockIdx.x * rows_per_step + lr; r < N; r += (long long)gridDim.x * rows_per_step) {
+            float x[8];
+            Vec8<float>::load(src + r * C + pc, x);
+            Vec8<T>::store(g_qkv + r * 3 * C + col, x);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += x[i];
+        }
+    }
+    if (!bias_partial) return;
+    // deterministic column sums: per-CTA partial [3C] (rows of this CTA in a fixed order), the caller adds the partials
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = active ? acc[i] : 0.f;
+    __syncthreads();
+    for (int c = threadIdx.x; c < 3 * C; c += kQkvThreads) {
+        const int g = c / 8, i = c % 8;
+        float s = 0.f;
+        for (int l = 0; l < rows_per_step; ++l) s += red[(l * G + g) * 8 + i];
+        bias_partial[(size_t)blockIdx.x * 3 * C + c] = s;
+    }
+}
+
+static int qkv_grid(int N, int rows_per_step) {
+    const long long need = ((long long)N + rows_per_step - 1) / rows_per_step;
+    const long long cap = 8LL * kNumSMs;   // 8 resident CTAs of 256 threads per SM
+    return (int)(need < cap ? (need < 1 ? 1 : need) : cap);
+}
+
+}  // namespace stb200
+
+using namespace stb200;
+
+extern "C" {
+
+int stb200_qkv_partial_rows(int N, int C) {
+    if (N <= 0 || C <= 0 || C % 8 || 3 * C / 8 > kQkvThreads) return 0;
+    return qkv_grid(N, kQkvThreads / (3 * C / 8));
+}
+
+int stb200_qkv_split(int N, int C, int dtype, const void *qkv, const float *bias, float *q, float *k, float *v, void *stream) {
+    STB200_REQUIRE(N > 0 && C > 0 && C % 8 == 0 && 3 * C / 8 <= kQkvThreads, STB200_ERR_ARG,
+                   "qkv_split: C must be a multiple of 8 with 3C <= %d (got %d)", 8 * kQkvThreads, C);
+    STB200_REQUIRE(qkv && q && k && v, STB200_ERR_ARG, "null pointer");
+    const int rps = kQkvThreads / (3 * C / 8), grid = qkv_grid(N, rps);
+    cudaStream_t s = (cudaStream_t)stream;
+    const double esz = dtype == 0 ? 4.0 : 2.0;
+    KernelScope ks("qkv_split", (double)N * 3 * C * (esz + 4.0), s);
+    if (dtype == 0) qkv_split_kernel<float><<<grid, kQkvThreads, 0, s>>>(N, C, (const float *)qkv, bias, q, k, v, rps);
+    else if (dtype == 1) qkv_split_kernel<__nv_bfloat16><<<grid, kQkvThreads, 0, s>>>(N, C, (const __nv_bfloat16 *)qkv, bias, q, k, v, rps);
+    else if (dtype == 2) qkv_split_kernel<__half><<<grid, kQkvThreads, 0, s>>>(N, C, (const __half *)qkv, bias, q, k, v, rps);
+    else { set_error("qkv_split: dtype %d (0 = fp32, 1 = bf16, 2 = fp16)", dtype); return STB200_ERR_ARG; }
+    return check_launch("qkv_split");
+}
+
+int stb200_qkv_merge(int N, int C, int dtype, const float *gq, const float *gk, const float *gv, void *g_qkv, float *bias_partial,
+                     void *stream) {
+    STB200_REQUIRE(N > 0 && C > 0 && C % 8 == 0 && 3 * C / 8 <= kQkvThreads, STB200_ERR_ARG,
+                   "qkv_merge: C must be a multiple of 8 with 3C <= %d (got %d)", 8 * kQkvThreads, C);
+    STB200_REQUIRE(gq && gk && gv && g_qkv, STB200_ERR_ARG, "null pointer");
+    const int rps = kQkvThreads / (3 * C / 8), grid = qkv_grid(N, rps);
+    cudaStream_t s = (cudaStream_t)stream;
+    const double esz = dtype == 0 ? 4.0 : 2.0;
+    KernelScope ks("qkv_merge", (double)N * 3 * C * (esz + 4.0), s);
+    if (dtype == 0) qkv_merge_kernel<float><<<grid, kQkvThreads, 0, s>>>(N, C, gq, gk, gv, (float *)g_qkv, bias_partial, rps);
+    else if (dtype == 1) qkv_merge_kernel<__nv_bfloat16><<<grid, kQkvThreads, 0, s>>>(N, C, gq, gk, gv, (__nv_bfloat16 *)g_qkv, bias_partial, rps);
+    else if (dtype == 2) qkv_merge_kernel<__half><<<grid, kQkvThreads, 0, s>>>(N, C, gq, gk, gv, (__half *)g_qkv, bias_partial, rps);
+    else { set_error("qkv_merge: dtype %d (0 = fp32, 1 = bf16, 2 = fp16)", dtype); return STB200_ERR_ARG; }
+    return check_launch("qkv_merge");
+}
+
+}  // extern "C"

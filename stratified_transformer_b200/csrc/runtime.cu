@@ -118,5 +118,5 @@ size_t stb200_profile_dump(char *buf, size_t cap) {
 
 const char *stb200_last_error(void) { return stb200::g_err; }
 long long stb200_launch_count(void) { return stb200::g_launches.load(std::memory_order_relaxed); }
-int stb200_version(void) { return 102; }   // 101: stb200_index gained len_order / t_len_order; 102: fused plan + fused attention
+int stb200_version(void) { return 103; }   // 101: stb200_index gained len_order / t_len_order; 102: fused plan + fused attention; 103: qkv split / merge
 }

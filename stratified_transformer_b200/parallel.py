@@ -34,21 +34,34 @@ def shard_batch(xyz: torch.Tensor, offset: torch.Tensor, rank: int, world_size: 
     return (xyz[sel], torch.cumsum(counts, 0).to(offset.dtype), *[t[sel] for t in per_point], ids)
 
 
-def allreduce_gradients(grads: Sequence[torch.Tensor], group=None, average: bool = True) -> None:
-    """In-place sum (or mean) of the given gradient tensors over all ranks with ONE collective."""
+def allreduce_gradients(grads: Sequence[torch.Tensor], group=None, average: bool = True, async_op: bool = False):
+    """In-place sum (or mean) of the given gradient tensors over all ranks with ONE collective.
+
+    async_op=True starts the collective and returns a `finish()` callable (None when there is nothing to reduce): the
+    exchange of one layer's gradients then runs on the backend's own stream under the backward pass of the next layers,
+    and `finish()` - called once at the end of the step - waits for it and writes the result back into the tensors."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return
+        return None
     grads = [g for g in grads if g is not None]
     if not grads:
-        return
+        return None
     flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, group=group)
-    if average:
-        flat /= dist.get_world_size(group)
-    o = 0
-    for g in grads:
-        g.copy_(flat[o:o + g.numel()].view_as(g))
-        o += g.numel()
+    work = dist.all_reduce(flat, group=group, async_op=async_op)
+
+    def finish():
+        if work is not None:
+            work.wait()
+        if average:
+            flat.div_(dist.get_world_size(group))
+        o = 0
+        for g in grads:
+            g.copy_(flat[o:o + g.numel()].view_as(g))
+            o += g.numel()
+
+    if async_op:
+        return finish
+    finish()
+    return None
 
 
 def global_throughput(points_local: int, seconds_local: float, device=None, group=None) -> float:

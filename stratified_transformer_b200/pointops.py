@@ -381,6 +381,47 @@ def window_attention_plan(q, k, v, table_q, table_k, table_v, plan):
     return WindowAttentionPlan.apply(q, k, v, table_q, table_k, table_v, plan)
 
 
+_QKV_DTYPES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+
+
+class SplitQKV(Function):
+    """qkv [N, 3C] (fp32 / bf16 / fp16: the projection GEMM's output without bias) + bias [3C] -> q, k, v fp32 [N, h, C/h]
+    contiguous, in one kernel; backward: one kernel writes grad_qkv in qkv's dtype and the bias gradient.  Replaces the
+    reshape / permute / contiguous / multiply of model/stratified_transformer.py:172-175 and the `.float()` casts at the
+    pointops call sites (the caller folds `scale` into the q rows of weight and bias)."""
+
+    @staticmethod
+    def forward(ctx, qkv, bias, h):
+        qkv = qkv.contiguous()
+        N, C3 = qkv.shape
+        C = C3 // 3
+        if qkv.dtype not in _QKV_DTYPES or C3 != 3 * C or C % 8 or C % h:
+            raise ValueError(f"SplitQKV: unsupported qkv {tuple(qkv.shape)} {qkv.dtype} with {h} heads")
+        if bias is not None:
+            bias = bias.float().contiguous()
+        q, k, v = (torch.empty(N, h, C // h, dtype=torch.float32, device=qkv.device) for _ in range(3))
+        _cabi.call("stb200_qkv_split", N, C, _QKV_DTYPES[qkv.dtype], qkv.data_ptr(), None if bias is None else bias.data_ptr(),
+                   q.data_ptr(), k.data_ptr(), v.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        ctx.dtype, ctx.has_bias, ctx.shape = qkv.dtype, bias is not None, (N, C)
+        return q, k, v
+
+    @staticmethod
+    def backward(ctx, gq, gk, gv):
+        N, C = ctx.shape
+        gq, gk, gv = (g.float().contiguous() for g in (gq, gk, gv))
+        g_qkv = torch.empty(N, 3 * C, dtype=ctx.dtype, device=gq.device)
+        partial = None
+        if ctx.has_bias and ctx.needs_input_grad[1]:
+            partial = torch.empty(_cabi.load().stb200_qkv_partial_rows(N, C), 3 * C, dtype=torch.float32, device=gq.device)
+        _cabi.call("stb200_qkv_merge", N, C, _QKV_DTYPES[ctx.dtype], gq.data_ptr(), gk.data_ptr(), gv.data_ptr(), g_qkv.data_ptr(),
+                   None if partial is None else partial.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        return g_qkv, None if partial is None else partial.sum(0), None
+
+
+def split_qkv(qkv, bias, num_heads):
+    return SplitQKV.apply(qkv, bias, num_heads)
+
+
 @torch.no_grad()
 def window_attention_inference_bf16(q, k, v, table_q, table_k, table_v, pair_index, pre_cast=False):
     """Forward-only pair path with bf16 storage of q / k / v and of the staged tables (BASELINE config 3, inference):

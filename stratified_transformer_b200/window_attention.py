@@ -62,13 +62,19 @@ class WindowAttention(nn.Module):
             idx.rel_idx = rel_pos_index_stratified(xyz, idx.index_0_offsets, idx.index_1, self.window_size, self.quant_size)
         N, C = feats.shape
         h = self.num_heads
-        # same math as `qkv(feats).reshape(N,3,h,d).permute(1,0,2,3)` followed by `query * scale`, but q/k/v come out of
-        # three GEMMs already contiguous ([N, h, d]) and the scale is folded into the q projection: no M- or N-sized
-        # permute / multiply passes around the pair ops
+        # same math as `qkv(feats).reshape(N,3,h,d).permute(1,0,2,3).contiguous()` followed by `query * scale` and the
+        # `.float()` casts at the pointops call sites: ONE GEMM without bias (scale folded into the q rows of the weight),
+        # then one kernel that adds the bias and writes q, k, v as contiguous fp32 [N, h, d] (pointops.split_qkv); no other
+        # N-sized permute / multiply / cast pass around the pair ops, forward or backward
         Wm, bm = self.qkv.weight, self.qkv.bias
-        query = torch.nn.functional.linear(feats, Wm[:C] * self.scale, None if bm is None else bm[:C] * self.scale).view(N, h, C // h)
-        key = torch.nn.functional.linear(feats, Wm[C:2 * C], None if bm is None else bm[C:2 * C]).view(N, h, C // h)
-        value = torch.nn.functional.linear(feats, Wm[2 * C:], None if bm is None else bm[2 * C:]).view(N, h, C // h)
+        if C % 8 == 0:
+            w_all = torch.cat([Wm[:C] * self.scale, Wm[C:]], 0)
+            b_all = None if bm is None else torch.cat([bm[:C] * self.scale, bm[C:]], 0)
+            query, key, value = pointops.split_qkv(torch.nn.functional.linear(feats, w_all), b_all, h)
+        else:   # channel counts the split kernel does not take: three GEMMs whose outputs are already contiguous
+            query = torch.nn.functional.linear(feats, Wm[:C] * self.scale, None if bm is None else bm[:C] * self.scale).view(N, h, C // h)
+            key = torch.nn.functional.linear(feats, Wm[C:2 * C], None if bm is None else bm[C:2 * C]).view(N, h, C // h)
+            value = torch.nn.functional.linear(feats, Wm[2 * C:], None if bm is None else bm[2 * C:]).view(N, h, C // h)
         if idx.plan is not None and self.rel_query and self.rel_key and self.rel_value and C // h == 16 and \
                 not getattr(self, "per_op", False):
             # window-centric fused kernels: the whole pair path (logits + rel-pos bias + softmax + aggregation, and its

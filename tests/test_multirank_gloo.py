@@ -30,6 +30,12 @@ def _worker(rank, world, port, out):
         g1, g2 = torch.full((3, 2), float(rank + 1)), torch.arange(4.0) * (rank + 1)
         parallel.allreduce_gradients([g1, None, g2])
         assert torch.allclose(g1, torch.full((3, 2), 1.5)) and torch.allclose(g2, torch.arange(4.0) * 1.5)
+        # the same started early and finished later (one layer's exchange under the next layer's backward)
+        g3 = torch.full((5,), float(rank))
+        fin = parallel.allreduce_gradients([g3], async_op=True)
+        assert callable(fin)
+        fin()
+        assert torch.allclose(g3, torch.full((5,), 0.5))
         # whole-job throughput = total points / slowest rank
         thr = parallel.global_throughput(100 * (rank + 1), 1.0 + rank)
         assert abs(thr - 300 / 2.0) < 1e-9

@@ -754,6 +754,139 @@ __global__ void __launch_bounds__(kThreads, MINB) segment_softmax_bwd_hp_kernel(
     }
 }
 
+// Span variants (default for h <= 32): the rows of a CSR chunk are ONE contiguous span of the [M, h] array, so a CTA copies the
+// whole span of `rpc` consecutive rows into shared memory with 16-byte loads issued back to back (a few KB in flight per
+// CTA instead of one ~100-float row per warp behind a dependent offsets load), works on the rows from shared memory with
+// the head-major lane mapping above (same summation order, bit-identical results), and streams the span out again with
+// 16-byte stores.  Chunks whose span exceeds the buffer (very long rows) take the per-row path from global memory.
+#ifndef SPAN_EXP
+#define SPAN_EXP expf
+#endif
+constexpr int kSpanFloats = 8192;   // per staged array: 32 KB (forward) / 2 x 32 KB (backward) per CTA
+
+// copy [lo, hi) of src into sm (sm[0] <-> element lo - shift, shift = lo % 4), 16-byte accesses on the aligned interior
+__device__ __forceinline__ void span_load(float *sm, const float *__restrict__ src, const float *__restrict__ add, size_t lo, size_t hi) {
+    const size_t lo_al = lo & ~(size_t)3;
+    const int nvec = (int)((hi - lo_al + 3) / 4);
+    for (int vi = threadIdx.x; vi < nvec; vi += blockDim.x) {
+        const size_t g = lo_al + 4 * (size_t)vi;
+        if (g >= lo && g + 4 <= hi) {
+            float4 x = __ldg(reinterpret_cast<const float4 *>(src + g));
+            if (add) {
+                const float4 y = __ldg(reinterpret_cast<const float4 *>(add + g));
+                x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+            }
+            *reinterpret_cast<float4 *>(sm + 4 * vi) = x;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (g + e >= lo && g + e < hi) sm[4 * vi + e] = __ldg(src + g + e) + (add ? __ldg(add + g + e) : 0.f);
+        }
+    }
+}
+__device__ __forceinline__ void span_store(float *__restrict__ dst, const float *sm, size_t lo, size_t hi) {
+    const size_t lo_al = lo & ~(size_t)3;
+    const int nvec = (int)((hi - lo_al + 3) / 4);
+    for (int vi = threadIdx.x; vi < nvec; vi += blockDim.x) {
+        const size_t g = lo_al + 4 * (size_t)vi;
+        if (g >= lo && g + 4 <= hi) {
+            *reinterpret_cast<float4 *>(dst + g) = *reinterpret_cast<const float4 *>(sm + 4 * vi);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (g + e >= lo && g + e < hi) dst[g + e] = sm[4 * vi + e];
+        }
+    }
+}
+
+// BWD = false: out = softmax_seg(x [+ y]);  BWD = true: x = p, y = grad_p, out = p * (grad_p - <p, grad_p>_seg)
+template <int HP, bool BWD>
+__global__ void __launch_bounds__(kThreads) segment_softmax_span_kernel(int N, int h, const float *__restrict__ x, const float *__restrict__ y,
+                                                                        const int *__restrict__ offsets, float *__restrict__ out, int rpc) {
+    extern __shared__ __align__(16) float span_smem[];
+    float *sa = span_smem;                                    // [kSpanFloats + 4]
+    float *sb = span_smem + (kSpanFloats + 4);                // backward only
+    int *soff = reinterpret_cast<int *>(span_smem + (BWD ? 2 : 1) * (kSpanFloats + 4));   // [rpc + 1]
+    constexpr int SL = kWarp / HP;
+    const int lane = threadIdx.x % kWarp, warp = threadIdx.x / kWarp, nwarps = blockDim.x / kWarp;
+    const int hd = lane % HP, slot = lane / HP;
+    const bool on = hd < h;
+    const int n_chunks = (N + rpc - 1) / rpc;
+    for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const int r0 = c * rpc, nr = min(rpc, N - r0);
+        for (int i = threadIdx.x; i <= nr; i += blockDim.x) soff[i] = __ldg(offsets + r0 + i);
+        __syncthreads();
+        const int s0 = soff[0], s1 = soff[nr];
+        const size_t lo = (size_t)s0 * h, hi = (size_t)s1 * h;
+        const int shift = (int)(lo & 3);
+        const bool staged = hi - lo + 3 <= (size_t)kSpanFloats;
+        if (staged) {
+            span_load(sa, x, BWD ? nullptr : y, lo, hi);
+            if (BWD) span_load(sb, y, nullptr, lo, hi);
+            __syncthreads();
+        }
+        for (int rr = warp; rr < nr; rr += nwarps) {
+            const int start = soff[rr], len = soff[rr + 1] - start;
+            if (len <= 0) continue;
+            if (staged) {
+                float *ra = sa + (size_t)(start - s0) * h + shift + hd;
+                if (!BWD) {
+                    float mx = -INFINITY;
+                    for (int i = slot; on && i < len; i += SL) mx = fmaxf(mx, ra[i * h]);
+#pragma unroll
+                    for (int o = HP; o < kWarp; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                    float sum = 0.f;
+#pragma unroll 2
+                    for (int i = slot; on && i < len; i += SL) {
+                        const float e = SPAN_EXP(ra[i * h] - mx);
+                        ra[i * h] = e;
+                        sum += e;
+                    }
+#pragma unroll
+                    for (int o = HP; o < kWarp; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                    const float inv = 1.0f / sum;   // one division per (row, head); the products differ from e / sum by <= 1 ulp
+                    for (int i = slot; on && i < len; i += SL) ra[i * h] *= inv;
+                } else {
+                    const float *rb = sb + (size_t)(start - s0) * h + shift + hd;
+                    float dot = 0.f;
+                    for (int i = slot; on && i < len; i += SL) dot = fmaf(ra[i * h], rb[i * h], dot);
+#pragma unroll
+                    for (int o = HP; o < kWarp; o <<= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+                    for (int i = slot; on && i < len; i += SL) ra[i * h] = ra[i * h] * (rb[i * h] - dot);
+                }
+            } else {   // oversized chunk: the row straight from global memory
+                const size_t base = (size_t)start * h + hd;
+                if (!BWD) {
+                    float mx = -INFINITY;
+                    for (int i = slot; on && i < len; i += SL) mx = fmaxf(mx, x[base + (size_t)i * h] + (y ? y[base + (size_t)i * h] : 0.f));
+#pragma unroll
+                    for (int o = HP; o < kWarp; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                    float sum = 0.f;
+                    for (int i = slot; on && i < len; i += SL) sum += expf(x[base + (size_t)i * h] + (y ? y[base + (size_t)i * h] : 0.f) - mx);
+#pragma unroll
+                    for (int o = HP; o < kWarp; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                    for (int i = slot; on && i < len; i += SL)
+                        out[base + (size_t)i * h] = expf(x[base + (size_t)i * h] + (y ? y[base + (size_t)i * h] : 0.f) - mx) / sum;
+                } else {
+                    float dot = 0.f;
+                    for (int i = slot; on && i < len; i += SL) dot = fmaf(x[base + (size_t)i * h], y[base + (size_t)i * h], dot);
+#pragma unroll
+                    for (int o = HP; o < kWarp; o <<= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+                    for (int i = slot; on && i < len; i += SL) {
+                        const size_t o2 = base + (size_t)i * h;
+                        out[o2] = x[o2] * (y[o2] - dot);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (staged) {
+            span_store(out, sa, lo, hi);
+            __syncthreads();
+        }
+    }
+}
+
 // dst[t, :] = src[perm[t], :]  (rows of h floats): per-pair weights into transposed-CSR order
 __global__ void permute_rows_kernel(int M, int h, const float *__restrict__ src, const int *__restrict__ perm,
                                     float *__restrict__ dst) {
@@ -791,7 +924,7 @@ static void launch_softmax_fwd_hp1(int blocks, cudaStream_t s, int N, int h, con
         case 1: segment_softmax_fwd_hp_kernel<HP, 2, 4><<<blocks, kThreads, 0, s>>>(N, h, a, b, off, p, rows); break;
         case 2: segment_softmax_fwd_hp_kernel<HP, 2, 6><<<blocks, kThreads, 0, s>>>(N, h, a, b, off, p, rows); break;
         case 3: segment_softmax_fwd_hp_kernel<HP, 1, 8><<<blocks, kThreads, 0, s>>>(N, h, a, b, off, p, rows); break;
-        default: segment_softmax_fwd_hp_kernel<HP, 1, 1><<<blocks, kThreads, 0, s>>>(N, h, a, b, off, p, rows); break;
+        default: segment_softmax_fwd_hp_kernel<HP, 1, 1><<<blocks, kThreads, 0, s>>>(N, h, a, b, off, p, rows); break;   // 4 (and the rows variant)
     }
 }
 static void launch_softmax_fwd_hp(int blocks, cudaStream_t s, int N, int h, const float *a, const float *b, const int *off,
@@ -859,6 +992,36 @@ static int prep_smem(K kernel, size_t bytes) {
     }
     return STB200_OK;
 }
+
+// span kernels: rows per chunk so that a chunk's span is about half the staging buffer on average
+template <bool BWD>
+static int launch_softmax_span(cudaStream_t s, int N, long long M, int h, const float *x, const float *y, const int *off, float *out) {
+    if (((uintptr_t)x | (uintptr_t)(y ? y : x) | (uintptr_t)out) & 15) return -1;   // unaligned views: per-row kernels
+    const double per_row = (double)M * h / max(1, N);
+    const int rpc = (int)max(2.0, min(64.0, (kSpanFloats / 2) / max(1.0, per_row)));
+    const size_t smem = (size_t)(BWD ? 2 : 1) * (kSpanFloats + 4) * sizeof(float) + (size_t)(rpc + 1) * sizeof(int);
+    const int n_chunks = (N + rpc - 1) / rpc;
+    const int per_sm = (int)min((size_t)8, (size_t)(200 * 1024) / smem);
+    const int blocks = max(1, min(n_chunks, kNumSMs * per_sm));
+#define STB200_SPAN(HP)                                                                                                         \
+    do {                                                                                                                        \
+        static bool attr = false;                                                                                               \
+        if (!attr) {                                                                                                            \
+            if (int rc = prep_smem(segment_softmax_span_kernel<HP, BWD>, (size_t)2 * (kSpanFloats + 4) * sizeof(float) + 65 * sizeof(int))) return rc; \
+            attr = true;                                                                                                        \
+        }                                                                                                                       \
+        segment_softmax_span_kernel<HP, BWD><<<blocks, kThreads, smem, s>>>(N, h, x, y, off, out, rpc);                         \
+    } while (0)
+    if (h <= 1) STB200_SPAN(1);
+    else if (h <= 2) STB200_SPAN(2);
+    else if (h <= 4) STB200_SPAN(4);
+    else if (h <= 8) STB200_SPAN(8);
+    else if (h <= 16) STB200_SPAN(16);
+    else STB200_SPAN(32);
+#undef STB200_SPAN
+    return STB200_OK;
+}
+
 
 // heads per CTA: as many as divide h, up to 4, while the staged tables stay under ~100 KB
 static int pick_hg(int h, int D, int L, int ntables) {
@@ -1115,7 +1278,11 @@ int stb200_segment_softmax_forward(int N, int M, int h, const float *a, const fl
     {
         KernelScope ks("segment_softmax_fwd", 4.0 * M * h * (b ? 3 : 2) + 4.0 * (N + 1), (cudaStream_t)stream);
         cudaStream_t s = (cudaStream_t)stream;
-        if (h <= 32) launch_softmax_fwd_hp(blocks, s, N, h, a, b, index0_offsets, p);
+        int rc = -1;
+        if (h <= 32 && softmax_variant() == 0) rc = launch_softmax_span<false>(s, N, M, h, a, b, index0_offsets, p);
+        if (rc > 0) return rc;
+        if (rc == 0) {}
+        else if (h <= 32) launch_softmax_fwd_hp(blocks, s, N, h, a, b, index0_offsets, p);
         else segment_softmax_fwd_kernel<<<blocks, kThreads, 0, s>>>(N, h, a, b, index0_offsets, p);
     }
     return check_launch("segment_softmax_fwd");
@@ -1144,7 +1311,13 @@ int stb200_segment_softmax_backward(int N, int M, int h, const float *p, const f
     {
         KernelScope ks("segment_softmax_bwd", 4.0 * M * h * 3 + 4.0 * (N + 1), (cudaStream_t)stream);
         cudaStream_t s = (cudaStream_t)stream;
-        if (h <= 32) launch_softmax_bwd_hp(blocks, s, N, h, p, grad_p, index0_offsets, grad_s);
+        int rc = -1;
+        // the per-row kernel streams at 3.3 TB/s on layer 0; the span version measured 2.0 TB/s (two staged arrays, three
+        // CTAs per SM): used only on request (STB200_SOFTMAX_VARIANT=5)
+        if (h <= 32 && softmax_variant() == 5) rc = launch_softmax_span<true>(s, N, M, h, p, grad_p, index0_offsets, grad_s);
+        if (rc > 0) return rc;
+        if (rc == 0) {}
+        else if (h <= 32) launch_softmax_bwd_hp(blocks, s, N, h, p, grad_p, index0_offsets, grad_s);
         else segment_softmax_bwd_kernel<<<blocks, kThreads, 0, s>>>(N, h, p, grad_p, index0_offsets, grad_s);
     }
     return check_launch("segment_softmax_bwd");

@@ -44,7 +44,7 @@ const char *stb200_last_error(void);
 /* number of kernels this library launched since load (bench.py's "gpu_launches") */
 long long stb200_launch_count(void);
 /* ABI version: 100 = first release, 101 = stb200_index has len_order / t_len_order (append-only struct growth),
- * 102 = fused work plan + fused window attention entry points; 103 = stb200_qkv_split / _merge */
+ * 102 = fused work plan + fused window attention entry points; 103 = stb200_qkv_split / _merge, pre-step (batch vector, ball query) */
 int stb200_version(void);
 /* Optional per-kernel profiler: when enabled every launch is bracketed by CUDA events on its stream.
  * stb200_profile_dump writes a JSON object {"kernel name": {"launches", "ms", "bytes"}} (bytes = algorithmic bytes
@@ -332,6 +332,20 @@ int stb200_qkv_partial_rows(int N, int C);
 int stb200_qkv_split(int N, int C, int dtype, const void *qkv, const float *bias, float *q, float *k, float *v, void *stream);
 int stb200_qkv_merge(int N, int C, int dtype, const float *grad_q, const float *grad_k, const float *grad_v, void *grad_qkv,
                      float *bias_partial, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Host pre-step of the training loop on the device — replaces train.py:319-325.
+ * stb200_batch_from_offset: batch[i] = scene of point i (the reference builds it with a Python list per scene); offset = cumulative
+ *     scene ends [b], int32; batch int64 [N] like the reference's `.long()`.
+ * stb200_ball_query: tp.ball_query(radius, max_num, x, y, mode="partial_dense", batch_x, batch_y) of torch_points_kernels (third
+ *     party, absent; its CPU path keeps max_num matches in kd-tree traversal order = unspecified).  Here: for query y[i] the
+ *     support points x[j] of the same scene with d^2 < radius^2 (fp32, (dx*dx + dy*dy) + dz*dz), ordered by (d^2, j), the first
+ *     max_num (<= 64) of them in idx [Ny, max_num] (int64, -1 padded) and dist2 [Ny, max_num] (-1 padded; may be NULL).
+ *     batch_x / batch_y NULL: one scene. */
+int stb200_batch_from_offset(int N, int b, const int *offset, long long *batch, void *stream);
+size_t stb200_ball_query_workspace_bytes(int Nx);
+int stb200_ball_query(int Nx, int Ny, float radius, int max_num, const float *x, const float *y, const long long *batch_x,
+                      const long long *batch_y, void *workspace, size_t workspace_bytes, long long *idx, float *dist2, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * k nearest neighbours per scene — replaces knnquery_cuda_launcher

@@ -79,6 +79,8 @@ _SIGNATURES = {
     "stb200_tc_selftest": [_c_int] * 4 + [P] * 5,
     "stb200_qkv_split": [_c_int] * 3 + [P] * 6,
     "stb200_qkv_merge": [_c_int] * 3 + [P] * 6,
+    "stb200_batch_from_offset": [_c_int, _c_int, P, P, P],
+    "stb200_ball_query": [_c_int, _c_int, ctypes.c_float, _c_int, P, P, P, P, P, _c_size_t, P, P, P],
     "stb200_set_torch_semantics": [_c_int],
     "stb200_rel_pos_index_swin": [_c_int, P, P, P, ctypes.c_float, ctypes.c_float, ctypes.c_float, _c_int, P, P, P, P],
 }
@@ -93,6 +95,7 @@ _RESTYPES = {
     "stb200_fused_max_keys": (_c_int, []),
     "stb200_fused_plan_scratch_bytes": (_c_size_t, [_c_int]),
     "stb200_qkv_partial_rows": (_c_int, [_c_int, _c_int]),
+    "stb200_ball_query_workspace_bytes": (_c_size_t, [_c_int]),
     "stb200_profile_enable": (None, [_c_int]),
     "stb200_profile_dump": (_c_size_t, [ctypes.c_char_p, _c_size_t]),
 }

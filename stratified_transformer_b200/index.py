@@ -10,6 +10,7 @@ The reference rebuilds the pair list for every block although only two distinct 
 from __future__ import annotations
 
 import os
+import warnings
 from dataclasses import dataclass, field
 
 import torch
@@ -115,10 +116,14 @@ def _plan_count(N, has_sparse, ws, blocks):
     return scratch, totals
 
 
-def _plan_fill(N, xyz, window_size, quant_size, n_win, n_samp, ws, scratch, totals_dev, totals, blocks, swin_shift=None) -> FusedPlan:
+def _plan_fill(N, xyz, window_size, quant_size, n_win, n_samp, ws, scratch, totals_dev, totals, blocks, swin_shift=None):
+    """FusedPlan, or None when the window structure is outside what the fused kernels take (a window that needs more than
+    _PLAN_MAXORD key chunks, i.e. more than 512 points in one small window / sampled keys in one large window, or more than
+    2^31 tile words): the caller then builds the CSR pair list and the per-op kernels run - another CUDA path, not a CPU one."""
     if totals[5]:
-        raise _cabi.Stb200Error(f"fused plan: unsupported window structure (error bits {totals[5]}: a window needs more than "
-                                f"{_PLAN_MAXORD} key chunks, or more than 2^31 tile words)")
+        warnings.warn(f"fused plan not applicable to this geometry (error bits {totals[5]}: a window needs more than "
+                      f"{_PLAN_MAXORD} key chunks, or more than 2^31 tile words); using the per-op pair-list kernels", stacklevel=3)
+        return None
     dev = xyz.device
     has_sparse = n_samp > 0
 
@@ -282,7 +287,7 @@ def build_stratified_index(xyz: torch.Tensor, offset: torch.Tensor, window_size:
     plan = None
     if fused:
         plan = _plan_fill(N, xyz, window_size, quant_size, n_win, m, workspace, plan_part[0], plan_part[1], ptot, FUSED_BLOCKS, swin_shift)
-        if not csr:
+        if not csr and plan is not None:
             return PairIndex(None, None, None, int(n_max), int(M), None, plan.order_s, plan.wstart_s, int(n_win), plan)
     index_1 = torch.empty(M, dtype=torch.int32, device=dev)
     rel_idx = torch.empty(M, 3, dtype=torch.int32, device=dev) if quant_size is not None else None
@@ -406,7 +411,7 @@ class PendingLayerIndex:
             if self.fused:
                 plan = _plan_fill(self.N, self.xyz, self.window_size, self.quant_size, n_win, self.m, ws, plan_part[0], plan_part[1],
                                   hl[4:], FUSED_BLOCKS)
-                if not self.csr:
+                if not self.csr and plan is not None:
                     built.append(PairIndex(None, None, None, int(n_max), int(M), None, plan.order_s, plan.wstart_s, int(n_win), plan))
                     continue
             index_1 = torch.empty(M, dtype=torch.int32, device=dev)

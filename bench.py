@@ -556,6 +556,7 @@ class HotPathModel(torch.nn.Module):
     def __init__(self, fused=True):
         super().__init__()
         self.fused = fused
+        self.after_level = None      # (level, callable): called once the forward of that level has been enqueued
         from stratified_transformer_b200.window_attention import WindowAttention
         self.stem = torch.nn.Linear(6, LAYERS[0]["C"])
         self.down = torch.nn.ModuleList([torch.nn.Linear(LAYERS[i]["C"], LAYERS[i + 1]["C"]) for i in range(len(LAYERS) - 1)])
@@ -573,6 +574,8 @@ class HotPathModel(torch.nn.Module):
                                                                           fused=self.fused, csr=not self.fused)
             for blk, attn in enumerate(self.blocks[lvl]):
                 feats = feats + attn(feats, xyzs[lvl], li.for_block(blk))
+            if self.after_level is not None and self.after_level[0] == lvl:
+                self.after_level[1]()
         return feats.float().pow(2).mean()
 
 
@@ -629,11 +632,18 @@ def main():
         pf = st_index.GeometryPrefetcher(geo_cfgs, dev, fused=use_fused, csr=not use_fused)
         pf.submit(xyzs_d, offs_d, offs_h)
 
+    # geometry of the next batch starts after this attention layer has been enqueued (-1: at the top of the step).  Layers 0/1
+    # are the kernels that fill the machine; FPS (64 SMs for ~11 ms) costs less beside the small deep-layer launches.
+    # Measured (profiles/r2_geometry_submit_point.txt): 8 scenes 71.9 -> 70.4 ms, 4 scenes 38.25 -> 37.1 ms when submitted after
+    # layer 1; with 1-2 scenes per GPU the step is too short for that (FPS alone is ~10 ms) and the top of the step is best.
+    geom_after = min(int(os.environ.get("STB200_BENCH_GEOM_AFTER_LEVEL", "1" if a.scenes >= 4 else "-1")), len(levels) - 2)
+
     def one_step():
         geo = None
         if pf is not None:
             geo = pf.take()
-            pf.submit(xyzs_d, offs_d, offs_h)
+            if geom_after < 0:
+                pf.submit(xyzs_d, offs_d, offs_h)
         # training only: data-parallel all-reduce of the attention parameters' gradients (parallel.py), started per layer as
         # soon as the layer's last block has been differentiated and finished at the end of the step
         pending = []
@@ -645,6 +655,15 @@ def main():
                 fin = parallel.allreduce_gradients([t for trip in level_grads for t in trip], average=True, async_op=True)
                 if fin is not None:
                     pending.append(fin)
+        if pf is not None and geom_after >= 0:
+            exchange, seen = on_level, [0]
+
+            def on_level(level_grads):
+                if seen[0] == geom_after:
+                    pf.submit(xyzs_d, offs_d, offs_h)
+                seen[0] += 1
+                if exchange is not None:
+                    exchange(level_grads)
         if use_fused:
             if geo is None:
                 geo = [st_index.build_layer_index(lv["xyz"], lv["offset"], lv["cfg"]["window"], lv["cfg"]["quant"], DS_SCALE,
@@ -698,7 +717,7 @@ def main():
     e2e = None
     if not a.no_e2e:
         torch.manual_seed(0)
-        model = HotPathModel(use_fused).to(dev)
+        model = core = HotPathModel(use_fused).to(dev)
         if dist is not None:
             model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])
         host = dict(feat6=torch.cat([rgb, levels[0]["xyz"].cpu()], 1).pin_memory(),
@@ -729,8 +748,14 @@ def main():
                 cur, geo = state["next"], pf2.take()
                 for t in [cur["feat6"]] + cur["xyz"] + cur["off"] + [s for s in cur["sub"] if s is not None]:
                     t.record_stream(main)
-                state["next"] = upload(pf2.side)
-                pf2.submit(state["next"]["xyz"], state["next"]["off"], offs_h)
+                state["next"] = upload(pf2.side)      # H2D of the next batch starts now, on the side stream
+
+                def submit_next():                     # its geometry after the forward of the machine-filling layers 0/1
+                    pf2.submit(state["next"]["xyz"], state["next"]["off"], offs_h)
+                if geom_after < 0:
+                    submit_next()
+                else:
+                    core.after_level = (geom_after, submit_next)
             else:
                 cur, geo = upload(main), None
             model.zero_grad(set_to_none=True)

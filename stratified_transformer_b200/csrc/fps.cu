@@ -419,7 +419,8 @@ extern "C" int stb200_furthestsampling(int b, int n, const float *xyz, const int
     // All clusters together take at most half of the SMs: the kernel is latency-bound (one CTA per SM, few issue
     // slots used) and normally runs beside the attention kernels of the previous batch (GeometryPrefetcher); 8 scenes
     // x 8 CTAs x 256 threads cost 8 % more FPS time than 16 x 128 but 2.4 % less step time in that pipeline.
-    while (cs < env_int("STB200_FPS_CLUSTER", kMaxCluster) && b * cs * 2 <= kNumSMs / 2 && cs * threads * per_thread < n) cs <<= 1;
+    const int max_sms = env_int("STB200_FPS_MAX_SMS", kNumSMs / 2);
+    while (cs < env_int("STB200_FPS_CLUSTER", kMaxCluster) && b * cs * 2 <= max_sms && cs * threads * per_thread < n) cs <<= 1;
     for (; cs >= 1; cs >>= 1) {
         // A thread's points are i = gtid + u * (cs * threads); "first strict maximum inside the thread" equals the
         // reference's tie order only if they all share i mod B, i.e. cs * threads must be a multiple of B.

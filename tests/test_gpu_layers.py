@@ -25,8 +25,19 @@ def _ref():
     return mod
 
 
+def _native():
+    """the WHOLE reference layer: its Python, its autograd functions (functions/pointops.py), its own kernels (libpointops2_ref.so)"""
+    path = os.path.join(ROOT, "oracle", "_ref", "ref_layers_native.py")
+    if not (os.path.exists(path) and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libpointops2_ref.so"))):
+        pytest.skip("oracle/_ref/ref_layers_native.py / libpointops2_ref.so not built (needs /root/reference at build time)")
+    spec = importlib.util.spec_from_file_location("ref_layers_native", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def _close(got, want, name, tol=2e-4):
-    got, want = got.detach().double(), want.detach().double()
+    got, want = got.detach().double().cpu(), want.detach().double().cpu()
     scale = max(1.0, float(want.abs().max()))
     err = float((got - want).abs().max())
     assert err <= tol * scale, f"{name}: max err {err:.3e} at scale {scale:.2f}"
@@ -105,3 +116,52 @@ def test_transition_down_offsets_carry_fractions_like_the_reference():
         count += ((off[i] - off[i - 1]) * 0.25) + 1
         want.append(count)
     assert transition_down_offsets(torch.tensor(off), 0.25) == [int(c) for c in want] == [251, 502, 754, 1006]
+
+
+def test_native_stand_ins_match_the_oracle():
+    """the torch voxel_grid / scatter_softmax stand-ins of the native reference module against the oracle's restatements"""
+    from oracle import attention_oracle as ao, index_oracle as io
+    nat = _native()
+    xyz, offset = _scene(2, 4000, 3)
+    batch = torch.from_numpy(io.batch_from_offset(offset.cpu().numpy())).cuda()
+    for w in (0.16, 0.32):
+        size = torch.tensor([w] * 3, device="cuda")
+        for pos, start in ((xyz, None), (xyz + 0.5 * size, xyz.min(0)[0])):
+            got = nat.voxel_grid(pos, batch, size, start)
+            want = io.voxel_grid(pos.cpu().numpy(), batch.cpu().numpy(), size.cpu().numpy(), None if start is None else start.cpu().numpy())
+            assert np.array_equal(got.cpu().numpy(), want)
+    i0 = torch.sort(torch.randint(0, 300, (5000,), device="cuda"))[0]
+    s = torch.randn(5000, 3, device="cuda") * 3
+    _close(nat.scatter_softmax(s, i0, dim=0), ao.softmax_fwd(s.double().cpu(), i0.cpu(), 300), "scatter_softmax stand-in", tol=1e-6)
+
+
+def test_native_reference_layer_matches_mirror():
+    """The mirror layer (device builder + libstb200) against the reference layer running entirely on its OWN code and kernels."""
+    from stratified_transformer_b200 import layers
+    nat = _native()
+    xyz, offset = _scene(2, 2500, 7)
+    C, h, window, quant, ds, depth = 48, 3, 0.32, 0.02, 8, 2
+    torch.manual_seed(3)
+    kw = dict(rel_query=True, rel_key=True, rel_value=True, drop_path=0.0, ratio=0.25, k=16, out_channels=96)
+    theirs = nat.BasicLayer(ds, depth, C, h, window, 0.04, quant, downsample=nat.TransitionDown, **kw).cuda()
+    for name, p in theirs.named_parameters():
+        if "relative_pos" in name:
+            torch.nn.init.uniform_(p, -0.3, 0.3)
+    mine = layers.BasicLayer(ds, depth, C, h, window, 0.04, quant, downsample=layers.TransitionDown, **kw).cuda()
+    mine.load_state_dict(theirs.state_dict())
+    feats = torch.randn(xyz.shape[0], C, device="cuda")
+
+    def run(layer):
+        layer.zero_grad(set_to_none=True)
+        f = feats.clone().requires_grad_(True)
+        out = layer(f, xyz, offset)
+        (out[0].square().sum() + out[3].square().sum()).backward()
+        return out, dict(gf=f.grad, **{n: p.grad for n, p in layer.named_parameters()})
+
+    (wf, _, _, wfd, wxd, wod), wg = run(theirs)
+    (gf, _, _, gfd, gxd, god), gg = run(mine)
+    assert torch.equal(gxd, wxd) and torch.equal(god.long().cpu(), wod.long().cpu())
+    _close(gf, wf, "feats")
+    _close(gfd, wfd, "feats_down")
+    for name in wg:
+        _close(gg[name], wg[name], f"grad {name}", tol=5e-4)

@@ -168,6 +168,54 @@ def workload_config(a, note=None):
 
 
 # ------------------------------------------------------------------------------------------------ reference-CUDA leg
+def ref_layer_leg(dev, reps=3):
+    """Layer-level like-for-like baseline, same run: the REFERENCE's whole `BasicLayer` (model/stratified_transformer.py:250-326 —
+    its per-forward Python derivation of the pair lists, its autograd functions from functions/pointops.py, its own kernels from
+    oracle/_ref; generated oracle/_ref/ref_layers_native.py, tests/test_gpu_layers.py checks the two layers agree) against this
+    package's drop-in `layers.BasicLayer`, forward + backward on ONE 80k-point scene with the layer-0 configuration of cfg2
+    (C=48, h=3, depth 2, window 0.16, quant 0.01, stratified keys ds=8, TransitionDown to 96 channels), same state dict and inputs.
+    torch_scatter / torch_geometric are absent: the reference side uses torch stand-ins for scatter_softmax and voxel_grid."""
+    import importlib.util
+    path = os.path.join(ROOT, "oracle", "_ref", "ref_layers_native.py")
+    if not (os.path.exists(path) and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libpointops2_ref.so"))):
+        return {"unavailable": "oracle/_ref/ref_layers_native.py / libpointops2_ref.so not built (needs /root/reference at build time)"}
+    spec = importlib.util.spec_from_file_location("ref_layers_native", path)
+    nat = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(nat)
+    from stratified_transformer_b200 import layers
+    from stratified_transformer_b200.synthetic import make_batch
+    xyz, _, offset = make_batch(1, 80000, seed0=7)
+    xd, od = torch.from_numpy(xyz).to(dev), torch.from_numpy(offset).to(dev)
+    cfg = LAYERS[0]
+    kw = dict(rel_query=True, rel_key=True, rel_value=True, drop_path=0.0, ratio=0.25, k=16, out_channels=LAYERS[1]["C"])
+    torch.manual_seed(0)
+    theirs = nat.BasicLayer(DS_SCALE, cfg["depth"], cfg["C"], cfg["h"], cfg["window"], 0.04, cfg["quant"], downsample=nat.TransitionDown, **kw).to(dev)
+    mine = layers.BasicLayer(DS_SCALE, cfg["depth"], cfg["C"], cfg["h"], cfg["window"], 0.04, cfg["quant"], downsample=layers.TransitionDown, **kw).to(dev)
+    mine.load_state_dict(theirs.state_dict())
+    feats = torch.randn(xd.shape[0], cfg["C"], device=dev)
+
+    def step(layer):
+        layer.zero_grad(set_to_none=True)
+        f = feats.clone().requires_grad_(True)
+        out = layer(f, xd, od)
+        (out[0].square().mean() + out[3].square().mean()).backward()
+
+    def timed(layer, n):
+        step(layer)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            step(layer)
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / n * 1e3
+    ref_ms, ours_ms = timed(theirs, reps), timed(mine, max(reps, 10))
+    return {"workload": f"BasicLayer fwd+bwd, 1 synthetic 80k-pt scene, layer 0 of cfg2 (C={cfg['C']}, h={cfg['h']}, depth {cfg['depth']}, "
+                        f"window {cfg['window']}, ds {DS_SCALE}) + TransitionDown; pair lists rebuilt every forward on both sides",
+            "ref_ms": round(ref_ms, 3), "ours_ms": round(ours_ms, 3), "speedup": round(ref_ms / ours_ms, 2),
+            "note": "reference = its own BasicLayer text, functions/pointops.py and kernels (oracle/_ref); wall clock with a device "
+                    "synchronize on both sides, host work (the reference's Python index construction) included"}
+
+
 def ref_cuda_leg(dev, reps=10):
     """The >= 10x target's denominator, measured in the same run (SURVEY 8d "Reference-GPU baseline"): the REFERENCE's own
     kernels (oracle/_ref = lib/pointops2/src/{attention_v2,rpe_v2}/*.cu compiled in place, unmodified launchers
@@ -856,6 +904,11 @@ def main():
             ref_cuda_baseline = ref_cuda_leg(dev)
         except Exception as exc:   # the leg is a reported comparison, never a reason to lose the bench line
             ref_cuda_baseline = {"error": f"{type(exc).__name__}: {exc}"}
+        try:
+            ref_cuda_baseline["layer"] = ref_layer_leg(dev)
+        except Exception as exc:
+            ref_cuda_baseline["layer"] = {"error": f"{type(exc).__name__}: {exc}"}
+        torch.cuda.empty_cache()
 
     line = {
         "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),

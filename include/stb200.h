@@ -354,6 +354,13 @@ int stb200_ball_query(int Nx, int Ny, float radius, int max_num, const float *x,
  * identical to the reference including the order of equal distances.  nsample <= 100 (the reference's heap size). */
 int stb200_knnquery(int m, int b, int nsample, const float *xyz, const float *new_xyz, const int *offset,
                     const int *new_offset, int *idx, float *dist2, void *stream);
+/* The same result through a grid-pruned search (support points sorted by (scene, cell); a query is settled from the cells around
+ * it when its k+1 nearest candidates are closer than the searched cube's faces and strictly ordered - then the answer is unique)
+ * with the exact heap scan above for whatever remains (ties, sparse neighbourhoods, scenes of at most k points, nsample > 32).
+ * n = number of support points; workspace from stb200_knnquery_workspace_bytes(n, m, b) (NULL: heap scan only). */
+size_t stb200_knnquery_workspace_bytes(int n, int m, int b);
+int stb200_knnquery_ws(int n, int m, int b, int nsample, const float *xyz, const float *new_xyz, const int *offset,
+                       const int *new_offset, int *idx, float *dist2, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * bf16-storage forward path (inference, BASELINE config 3): q / k / v are bf16 [N,h,16] (device pointers to

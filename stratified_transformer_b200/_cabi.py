@@ -68,6 +68,7 @@ _SIGNATURES = {
     "stb200_window_logits_forward_bf16": [_IX, _c_int, _c_int, _c_int] + [P] * 6,
     "stb200_window_aggregate_forward_bf16": [_IX, _c_int, _c_int, _c_int] + [P] * 5,
     "stb200_knnquery": [_c_int, _c_int, _c_int, P, P, P, P, P, P, P],
+    "stb200_knnquery_ws": [_c_int, _c_int, _c_int, _c_int, P, P, P, P, P, P, P, _c_size_t, P],
     "stb200_classify_windows": [_c_int, P, P, P, P, P, P, P, P],
     "stb200_window_attention_forward_fused": [_IX, _c_int, P, P, _c_int, _c_int, _c_int] + [P] * 9,
     "stb200_segment_softmax_forward_rows": [_c_int, P, _c_int, P, P, P, P, P],
@@ -96,6 +97,7 @@ _RESTYPES = {
     "stb200_fused_plan_scratch_bytes": (_c_size_t, [_c_int]),
     "stb200_qkv_partial_rows": (_c_int, [_c_int, _c_int]),
     "stb200_ball_query_workspace_bytes": (_c_size_t, [_c_int]),
+    "stb200_knnquery_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
     "stb200_profile_enable": (None, [_c_int]),
     "stb200_profile_dump": (_c_size_t, [ctypes.c_char_p, _c_size_t]),
 }

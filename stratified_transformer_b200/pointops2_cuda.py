@@ -13,6 +13,8 @@ from __future__ import annotations
 
 from collections import OrderedDict
 
+import os
+
 import torch
 
 from . import _cabi
@@ -232,6 +234,14 @@ def furthestsampling_cuda(b, n, xyz, offset, new_offset, tmp, idx):
 
 
 def knnquery_cuda(m, nsample, xyz, new_xyz, offset, new_offset, idx, dist2):
-    """same positional arguments as the reference pybind function (knnquery/knnquery_cuda_kernel.h:7)"""
-    _cabi.call("stb200_knnquery", int(m), int(offset.numel()), int(nsample), _f(xyz, "xyz"), _f(new_xyz, "new_xyz"),
-               _i(offset, "offset"), _i(new_offset, "new_offset"), _i(idx, "idx"), _f(dist2, "dist2"), _stream())
+    """same positional arguments as the reference pybind function (knnquery/knnquery_cuda_kernel.h:7); grid-pruned search with
+    the exact heap scan as its completion (include/stb200.h); STB200_KNN_BRUTE=1: heap scan only"""
+    n, b = int(xyz.shape[0]), int(offset.numel())
+    if os.environ.get("STB200_KNN_BRUTE"):
+        _cabi.call("stb200_knnquery", int(m), b, int(nsample), _f(xyz, "xyz"), _f(new_xyz, "new_xyz"),
+                   _i(offset, "offset"), _i(new_offset, "new_offset"), _i(idx, "idx"), _f(dist2, "dist2"), _stream())
+        return
+    nbytes = int(_cabi.load().stb200_knnquery_workspace_bytes(n, int(m), b))
+    ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=xyz.device)
+    _cabi.call("stb200_knnquery_ws", n, int(m), b, int(nsample), _f(xyz, "xyz"), _f(new_xyz, "new_xyz"), _i(offset, "offset"),
+               _i(new_offset, "new_offset"), _i(idx, "idx"), _f(dist2, "dist2"), ws.data_ptr(), nbytes, _stream())

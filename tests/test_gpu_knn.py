@@ -62,3 +62,29 @@ def test_queryandgroup_and_interpolation():
     wgt = 1.0 / (np.sqrt(d2) + 1e-8); wgt /= wgt.sum(1, keepdims=True)
     want = (sfeat.cpu().numpy()[idx3] * wgt[..., None]).sum(1)
     assert np.allclose(out.cpu().numpy(), want, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("n_scenes,n_pts,k,direction", [(2, 30000, 16, "down"), (1, 80000, 16, "down"), (2, 30000, 3, "up")])
+def test_knn_grid_search_matches_reference_kernel_on_scene_geometry(n_scenes, n_pts, k, direction):
+    """Room-like synthetic scenes (surfaces, empty space): the grid-pruned search + heap completion against the reference's own
+    kernel, both directions the model uses (TransitionDown: queries are a subset of the support; Upsample: the support is the
+    subset and most queries are not in it)."""
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref not built")
+    from stratified_transformer_b200 import pointops
+    from stratified_transformer_b200.synthetic import make_batch
+    xyz, _, offset = make_batch(n_scenes, n_pts, seed0=11)
+    starts = np.concatenate([[0], offset[:-1]])
+    sel = np.concatenate([np.arange(s, e)[::4] for s, e in zip(starts, offset)])
+    sub = xyz[sel].copy()
+    sub_off = np.cumsum([len(np.arange(s, e)[::4]) for s, e in zip(starts, offset)]).astype(np.int32)
+    if direction == "down":
+        sup, sup_off, qry, qry_off = xyz, offset, sub, sub_off
+    else:
+        sup, sup_off, qry, qry_off = sub, sub_off, xyz, offset
+    sd, qd = torch.from_numpy(sup).cuda(), torch.from_numpy(qry).cuda()
+    so, qo = torch.from_numpy(sup_off).cuda(), torch.from_numpy(qry_off).cuda()
+    idx, dist = pointops.knnquery(k, sd, qd, so, qo)
+    ridx, rd2 = ref_cuda.knnquery(k, sd, qd, so, qo)
+    assert torch.equal(idx, ridx)
+    assert torch.equal(dist, torch.sqrt(rd2))

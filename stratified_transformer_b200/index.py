@@ -249,6 +249,20 @@ def fps_new_offset(offset: torch.Tensor, downsample_scale: int) -> torch.Tensor:
     return torch.cumsum(torch.div(counts, downsample_scale, rounding_mode="floor") + 1, 0).to(torch.int32)
 
 
+def fps_prefix(long_idx: torch.Tensor, long_offset: torch.Tensor, short_offset: torch.Tensor) -> torch.Tensor:
+    """Furthest point sampling is greedy from point 0 of every scene, so the picks for a smaller sample count are the first
+    picks of a longer run over the same scenes.  long_idx: picks of the longer run, long_offset / short_offset: cumulative counts
+    per scene of the longer / the wanted run (short count <= long count in every scene).  Returns the shorter run's picks."""
+    lo = long_offset.to(torch.int64)
+    so = short_offset.to(device=lo.device, dtype=torch.int64)
+    long_start = lo - torch.diff(lo, prepend=lo.new_zeros(1))
+    short_cnt = torch.diff(so, prepend=so.new_zeros(1))
+    short_start = so - short_cnt
+    scene = torch.repeat_interleave(torch.arange(so.numel(), device=lo.device), short_cnt)
+    pos = torch.arange(int(so[-1]), device=lo.device) - short_start[scene] + long_start[scene]
+    return long_idx[pos].contiguous()
+
+
 def build_stratified_index(xyz: torch.Tensor, offset: torch.Tensor, window_size: float, quant_size: float | None,
                            downsample_idx: torch.Tensor | None, parity: int, want_index_0: bool = False,
                            workspace: torch.Tensor | None = None, fused: bool = False, csr: bool = True,
@@ -339,12 +353,13 @@ class LayerIndex:
 
 def build_layer_index(xyz: torch.Tensor, offset: torch.Tensor, window_size: float, quant_size: float,
                       downsample_scale: int | None, want_index_0: bool = False, parities=(0, 1), fused: bool = False,
-                      csr: bool = True) -> LayerIndex:
+                      csr: bool = True, downsample_idx: torch.Tensor | None = None) -> LayerIndex:
     """stratified_transformer.py:267-317 for one layer: FPS (n_i // ds + 1 samples per scene), then both parities.
-    downsample_scale=None -> dense-only pairs (Swin)."""
+    downsample_scale=None -> dense-only pairs (Swin).  downsample_idx: the FPS picks when the caller already has them
+    (`fps_prefix`: they are a prefix of any longer FPS run over the same scenes)."""
     offset = offset.to(device=xyz.device, dtype=torch.int32)
-    ds_idx = None
-    if downsample_scale is not None:
+    ds_idx = downsample_idx
+    if downsample_scale is not None and ds_idx is None:
         ds_idx = pointops.furthestsampling(xyz, offset, fps_new_offset(offset, downsample_scale))
     ws = torch.empty(_cabi.load().stb200_pair_builder_workspace_bytes(xyz.shape[0]), dtype=torch.uint8, device=xyz.device)
     built = {p: build_stratified_index(xyz, offset, window_size, quant_size, ds_idx, p, want_index_0, ws, fused, csr) for p in parities}

@@ -73,9 +73,16 @@ class TransitionDown(nn.Module):
         self.linear = nn.Linear(in_channels, out_channels, bias=False)
         self.pool = nn.MaxPool1d(k)
 
-    def forward(self, feats, xyz, offset):
-        n_offset = torch.tensor(transition_down_offsets(offset, self.ratio), dtype=torch.int32, device=xyz.device)
-        idx = pointops.furthestsampling(xyz, offset.int(), n_offset)
+    def sample_offsets(self, offset, device):
+        return torch.tensor(transition_down_offsets(offset, self.ratio), dtype=torch.int32, device=device)
+
+    def forward(self, feats, xyz, offset, fps=None):
+        """fps = (idx, n_offset): furthest-point picks the caller already computed for exactly these scenes and counts"""
+        if fps is None:
+            n_offset = self.sample_offsets(offset, xyz.device)
+            idx = pointops.furthestsampling(xyz, offset.int(), n_offset)
+        else:
+            idx, n_offset = fps
         n_xyz = xyz[idx.long(), :]
         grouped = pointops.queryandgroup(self.k, xyz, n_xyz, feats, None, offset.int(), n_offset, use_xyz=False)   # (m, k, c)
         m, k, c = grouped.shape
@@ -148,13 +155,25 @@ class BasicLayer(nn.Module):
         self.downsample = downsample(channel, out_channels, ratio, k) if downsample else None
 
     def forward(self, feats, xyz, offset, layer_index=None):
-        li = layer_index
+        li, fps = layer_index, None
         if li is None:
-            li = st_index.build_layer_index(xyz, offset, self.window_size, self.quant_size, self.downsample_scale, fused=self.fused)
+            ds_idx = None
+            if isinstance(self.downsample, TransitionDown) and self.downsample_scale is not None:
+                # The reference samples twice per layer from the same points: n // ds + 1 key candidates here (line 289) and
+                # ratio * n + 1 points in TransitionDown (line 103).  FPS is greedy from point 0 of each scene, so the shorter
+                # list is a prefix of the longer one: ONE run serves both (a third of the layer's FPS iterations saved).
+                n_offset = self.downsample.sample_offsets(offset, xyz.device)
+                k_offset = st_index.fps_new_offset(offset.to(xyz.device), self.downsample_scale)
+                if bool((torch.diff(k_offset, prepend=k_offset.new_zeros(1)) <= torch.diff(n_offset, prepend=n_offset.new_zeros(1))).all()):
+                    fps = (pointops.furthestsampling(xyz, offset.int(), n_offset), n_offset)
+                    ds_idx = st_index.fps_prefix(fps[0], n_offset, k_offset)
+            li = st_index.build_layer_index(xyz, offset, self.window_size, self.quant_size, self.downsample_scale, fused=self.fused,
+                                            downsample_idx=ds_idx)
         for i, blk in enumerate(self.blocks):
             feats = blk(feats, xyz, li.for_block(i))
         if self.downsample:
-            feats_down, xyz_down, offset_down = self.downsample(feats, xyz, offset)
+            feats_down, xyz_down, offset_down = self.downsample(feats, xyz, offset, fps) if fps is not None else \
+                self.downsample(feats, xyz, offset)
         else:
             feats_down, xyz_down, offset_down = None, None, None
         return feats, xyz, offset, feats_down, xyz_down, offset_down

@@ -98,3 +98,17 @@ def test_fps_large_batches_fall_back_to_streaming(b, n_big):
     new_offset = io.fps_new_offset(offset, 64)
     want = fps_oracle.furthestsampling(xyz, offset, new_offset)
     assert np.array_equal(ours(xyz, offset, new_offset), want)
+
+
+def test_shorter_fps_run_is_a_prefix_of_the_longer_one():
+    """index.fps_prefix: the picks for n // 8 + 1 samples are the first picks of the run for n // 4 + 1 samples, per scene
+    (what layers.BasicLayer uses to run FPS once per layer instead of twice)."""
+    from stratified_transformer_b200 import index, pointops
+    from stratified_transformer_b200.synthetic import make_batch
+    xyz, _, offset = make_batch(3, 6000, seed0=2, n_raw=100000)
+    xd, od = torch.from_numpy(xyz).cuda(), torch.from_numpy(offset).cuda()
+    long_off = index.fps_new_offset(od, 4)
+    short_off = index.fps_new_offset(od, 8)
+    long_idx = pointops.furthestsampling(xd, od, long_off)
+    want = pointops.furthestsampling(xd, od, short_off)
+    assert torch.equal(index.fps_prefix(long_idx, long_off, short_off), want)

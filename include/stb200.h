@@ -151,6 +151,14 @@ int stb200_attention_step2_with_rel_pos_value_backward(int N, int M, int h, int 
  * untouched (the running minimum distances live on chip); idx [new_offset[b-1]] int32 out. */
 int stb200_furthestsampling(int b, int n, const float *xyz, const int *offset, const int *new_offset,
                             float *tmp, int *idx, void *stream);
+/* The same sampling, bit for bit, with exact bounding-box pruning of the distance update (csrc/fps.cu, fps_pruned_kernel): the points
+ * of a scene are Morton-sorted into groups of 256 and a group is skipped while the new sample is at least as far from its box as
+ * its largest running minimum.  N = total number of points (all scenes); workspace from stb200_fps_workspace_bytes(N, b).
+ * Opt-in (STB200_FPS_PRUNE=1 in the environment; measured slower than the plain kernel on B200); without it,
+ * with workspace NULL or for scenes below 3072 points: identical to stb200_furthestsampling. */
+size_t stb200_fps_workspace_bytes(int N, int b);
+int stb200_furthestsampling_ws(int b, int n, int N, const float *xyz, const int *offset, const int *new_offset, float *tmp, int *idx,
+                               void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Pair-index construction (new: the reference does this in Python with torch ops + torch_geometric's

@@ -56,6 +56,7 @@ _SIGNATURES = {
     "stb200_attention_step2_with_rel_pos_value_forward": [_c_int] * 5 + [P] * 8,
     "stb200_attention_step2_with_rel_pos_value_backward": [_c_int] * 5 + [P] * 11,
     "stb200_furthestsampling": [_c_int, _c_int] + [P] * 6,
+    "stb200_furthestsampling_ws": [_c_int, _c_int, _c_int, P, P, P, P, P, P, _c_size_t, P],
     "stb200_stratified_pairs_count": [_c_int, _c_int, P, P, ctypes.c_float, _c_int, P, _c_int, P, _c_size_t, P, P, P],
     "stb200_stratified_pairs_fill": [_c_int, P, ctypes.c_float, ctypes.c_float, _c_int, P, _c_size_t, P, P, P, P, P, P, _c_int, _c_int, P],
     "stb200_rel_pos_index_stratified": [_c_int, P, P, P, ctypes.c_float, ctypes.c_float, P, P],
@@ -98,6 +99,7 @@ _RESTYPES = {
     "stb200_qkv_partial_rows": (_c_int, [_c_int, _c_int]),
     "stb200_ball_query_workspace_bytes": (_c_size_t, [_c_int]),
     "stb200_knnquery_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
+    "stb200_fps_workspace_bytes": (_c_size_t, [_c_int, _c_int]),
     "stb200_profile_enable": (None, [_c_int]),
     "stb200_profile_dump": (_c_size_t, [ctypes.c_char_p, _c_size_t]),
 }

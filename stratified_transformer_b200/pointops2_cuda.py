@@ -229,8 +229,13 @@ def furthestsampling_cuda(b, n, xyz, offset, new_offset, tmp, idx):
     register-resident cluster kernel; None allocates it here."""
     if tmp is None:
         tmp = torch.full((xyz.shape[0],), 1e10, dtype=torch.float32, device=xyz.device)
-    _cabi.call("stb200_furthestsampling", int(b), int(n), _f(xyz, "xyz"), _i(offset, "offset"),
-               _i(new_offset, "new_offset"), None if tmp is None else _f(tmp, "tmp"), _i(idx, "idx"), _stream())
+    # exact bounding-box pruning (include/stb200.h: stb200_furthestsampling_ws); the library itself falls back to the plain
+    # kernel for small scenes or STB200_FPS_PRUNE=0
+    N = int(xyz.shape[0])
+    nbytes = int(_cabi.load().stb200_fps_workspace_bytes(N, int(b)))
+    ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=xyz.device)
+    _cabi.call("stb200_furthestsampling_ws", int(b), int(n), N, _f(xyz, "xyz"), _i(offset, "offset"), _i(new_offset, "new_offset"),
+               None if tmp is None else _f(tmp, "tmp"), _i(idx, "idx"), ws.data_ptr(), nbytes, _stream())
 
 
 def knnquery_cuda(m, nsample, xyz, new_xyz, offset, new_offset, idx, dist2):

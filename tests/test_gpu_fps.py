@@ -112,3 +112,22 @@ def test_shorter_fps_run_is_a_prefix_of_the_longer_one():
     long_idx = pointops.furthestsampling(xd, od, long_off)
     want = pointops.furthestsampling(xd, od, short_off)
     assert torch.equal(index.fps_prefix(long_idx, long_off, short_off), want)
+
+
+def test_pruned_variant_is_bit_identical(monkeypatch):
+    """STB200_FPS_PRUNE=1: exact bounding-box pruning of the distance update (csrc/fps.cu, fps_pruned_kernel) - same picks as
+    the plain kernel on room-like scenes, a tie-saturated lattice and uniform noise, 1 and 4 scenes."""
+    from stratified_transformer_b200 import pointops
+    from stratified_transformer_b200.synthetic import make_batch
+    rng = np.random.default_rng(0)
+    cases = [make_batch(1, 80000, seed0=21)[::2], make_batch(4, 50000, seed0=22)[::2],
+             ((rng.integers(0, 40, (60000, 3)) * 0.05).astype(np.float32), np.array([60000], np.int32)),
+             (rng.random((70000, 3)).astype(np.float32), np.array([30000, 70000], np.int32))]
+    for xyz, offset in cases:
+        xd, od = torch.from_numpy(np.ascontiguousarray(xyz)).cuda(), torch.from_numpy(offset).cuda()
+        new_off = torch.cumsum(torch.diff(od, prepend=od.new_zeros(1)) // 8 + 1, 0).int()
+        monkeypatch.setenv("STB200_FPS_PRUNE", "0")
+        want = pointops.furthestsampling(xd, od, new_off)
+        monkeypatch.setenv("STB200_FPS_PRUNE", "1")
+        got = pointops.furthestsampling(xd, od, new_off)
+        assert torch.equal(got, want)

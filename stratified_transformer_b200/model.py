@@ -1,0 +1,191 @@
+"""The whole network around the hot path: drop-in mirrors of the reference's `KPConvSimpleBlock`, `KPConvResBlock`
+and `Stratified` (/root/reference/model/stratified_transformer.py:344-505), assembled from `layers.py` (BasicLayer /
+TransitionDown / Upsample on libstb200) with the reference's constructor arguments, attribute names and return values, so a
+reference checkpoint's `state_dict` loads.
+
+`KPConvLayer` and `FastBatchNorm1d` are torch_points3d classes (third party, not vendored: PARITY UNPINNED).  They are restated
+here from the published algorithm (rigid KPConv, linear influence, sum aggregation; Thomas et al. 2019 / torch_points3d
+`KPConv/kernels.py`, `convolution_ops.py`) with the library's parameter names (`K_points`, `weight`, `batch_norm.*`).  The
+kernel-point disposition the library loads from its optimised tables is replaced by a fixed symmetric one for fresh models;
+checkpoints bring their own `K_points`.  These stem blocks are plain torch operators: they are outside the hot path.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+from torch.nn.init import trunc_normal_
+
+from .layers import BasicLayer, TransitionDown, Upsample
+
+
+def default_kernel_points(radius: float, n: int = 15) -> torch.Tensor:
+    """A fixed symmetric disposition: the centre, the 6 axis directions and the 8 cube diagonals, at 2/3 of the kernel radius
+    (torch_points3d instead loads dispositions optimised offline; any checkpoint overrides these values)."""
+    dirs = [(0.0, 0.0, 0.0)]
+    for a in range(3):
+        for s in (1.0, -1.0):
+            d = [0.0, 0.0, 0.0]
+            d[a] = s
+            dirs.append(tuple(d))
+    c = 1.0 / math.sqrt(3.0)
+    for sx in (c, -c):
+        for sy in (c, -c):
+            for sz in (c, -c):
+                dirs.append((sx, sy, sz))
+    pts = torch.tensor(dirs[:n], dtype=torch.float32)
+    if n > len(dirs):   # more points than the fixed set: fill a Fibonacci sphere
+        k = torch.arange(n - len(dirs), dtype=torch.float32) + 0.5
+        phi = torch.acos(1 - 2 * k / (n - len(dirs)))
+        th = math.pi * (1 + 5 ** 0.5) * k
+        pts = torch.cat([pts, torch.stack([torch.cos(th) * torch.sin(phi), torch.sin(th) * torch.sin(phi), torch.cos(phi)], 1)])
+    return pts * (2.0 / 3.0) * radius
+
+
+class KPConvLayer(nn.Module):
+    """Rigid kernel-point convolution: out_i = sum_k ( sum_{j in N(i)} max(0, 1 - |x_j - x_i - K_k| / extent) f_j ) W_k.
+    Neighbour index -1 (padding of the radius search) is a shadow point far away with zero features."""
+    _INFLUENCE_TO_RADIUS = 1.5
+
+    def __init__(self, num_inputs, num_outputs, point_influence, n_kernel_points=15, fixed="center", KP_influence="linear",
+                 aggregation_mode="sum", dimension=3, add_one=False, **kwargs):
+        super().__init__()
+        if KP_influence != "linear" or aggregation_mode != "sum" or dimension != 3:
+            raise NotImplementedError("only the configuration the model uses: linear influence, sum aggregation, 3-D")
+        self.kernel_radius = self._INFLUENCE_TO_RADIUS * point_influence
+        self.point_influence = point_influence
+        self.add_one = add_one
+        self.num_inputs = num_inputs + self.add_one * 1
+        self.num_outputs = num_outputs
+        self.n_kernel_points = n_kernel_points
+        self.K_points = nn.Parameter(default_kernel_points(self.kernel_radius, n_kernel_points), requires_grad=False)
+        self.weight = nn.Parameter(torch.empty(n_kernel_points, self.num_inputs, num_outputs))
+        nn.init.xavier_normal_(self.weight)
+
+    def forward(self, query_points, support_points, neighbors, x):
+        n_sup = support_points.shape[0]
+        nb = neighbors.long()
+        nb = torch.where(nb < 0, torch.full_like(nb, n_sup), nb)                       # padding -> the shadow row
+        sup = torch.cat([support_points, torch.full_like(support_points[:1], 1e6)], 0)
+        rel = sup[nb] - query_points.unsqueeze(1)                                       # [n, nn, 3]
+        d = torch.linalg.vector_norm(rel.unsqueeze(2) - self.K_points, dim=3)           # [n, nn, K]
+        w = torch.clamp(1.0 - d / self.point_influence, min=0.0).transpose(1, 2)       # [n, K, nn]
+        feats = torch.cat([x, torch.zeros_like(x[:1])], 0)[nb]                          # [n, nn, Cin]
+        per_kernel = torch.matmul(w, feats).permute(1, 0, 2)                            # [K, n, Cin]
+        return torch.matmul(per_kernel, self.weight).sum(0)                             # [n, Cout]
+
+
+class FastBatchNorm1d(nn.Module):
+    """torch_points3d.core.common_modules.FastBatchNorm1d: BatchNorm1d over [N, C] (or [B, N, C]) inputs; the inner module is
+    called `batch_norm`, which is what the checkpoints' keys say."""
+
+    def __init__(self, num_features, momentum=0.1, **kwargs):
+        super().__init__()
+        self.batch_norm = nn.BatchNorm1d(num_features, momentum=momentum, **kwargs)
+
+    def forward(self, x):
+        if x.dim() == 2:
+            return self.batch_norm(x)
+        if x.dim() == 3:
+            return self.batch_norm(x.transpose(1, 2)).transpose(1, 2)
+        raise ValueError(f"FastBatchNorm1d: expected 2-D or 3-D input, got {x.dim()}-D")
+
+
+class KPConvSimpleBlock(nn.Module):
+    """stratified_transformer.py:344-360"""
+
+    def __init__(self, in_channels, out_channels, prev_grid_size, sigma=1.0, negative_slope=0.2, bn_momentum=0.02):
+        super().__init__()
+        self.kpconv = KPConvLayer(in_channels, out_channels, point_influence=prev_grid_size * sigma, add_one=False)
+        self.bn = FastBatchNorm1d(out_channels, momentum=bn_momentum)
+        self.activation = nn.LeakyReLU(negative_slope=negative_slope)
+
+    def forward(self, feats, xyz, batch, neighbor_idx):
+        return self.activation(self.bn(self.kpconv(xyz, xyz, neighbor_idx, feats)))
+
+
+class KPConvResBlock(nn.Module):
+    """stratified_transformer.py:363-396"""
+
+    def __init__(self, in_channels, out_channels, prev_grid_size, sigma=1.0, negative_slope=0.2, bn_momentum=0.02):
+        super().__init__()
+        d_2 = out_channels // 4
+        activation = nn.LeakyReLU(negative_slope=negative_slope)
+        self.unary_1 = nn.Sequential(nn.Linear(in_channels, d_2, bias=False), FastBatchNorm1d(d_2, momentum=bn_momentum), activation)
+        self.unary_2 = nn.Sequential(nn.Linear(d_2, out_channels, bias=False), FastBatchNorm1d(out_channels, momentum=bn_momentum),
+                                     activation)
+        self.kpconv = KPConvLayer(d_2, d_2, point_influence=prev_grid_size * sigma, add_one=False)
+        self.bn = FastBatchNorm1d(out_channels, momentum=bn_momentum)
+        self.activation = activation
+        if in_channels != out_channels:
+            self.shortcut_op = nn.Sequential(nn.Linear(in_channels, out_channels, bias=False),
+                                             FastBatchNorm1d(out_channels, momentum=bn_momentum))
+        else:
+            self.shortcut_op = nn.Identity()
+
+    def forward(self, feats, xyz, batch, neighbor_idx):
+        out = self.unary_2(self.kpconv(xyz, xyz, neighbor_idx, self.unary_1(feats)))
+        return out + self.shortcut_op(feats)
+
+
+class Stratified(nn.Module):
+    """stratified_transformer.py:399-505: KPConv stem -> BasicLayers with TransitionDown -> Upsample chain -> classifier and the
+    offset regressor of this fork.  forward(feats, xyz, offset, batch, neighbor_idx) -> (logits [N, num_classes], shift [N, 3])."""
+
+    def __init__(self, downsample_scale, depths, channels, num_heads, window_size, up_k, grid_sizes, quant_sizes, rel_query=True,
+                 rel_key=False, rel_value=False, drop_path_rate=0.2, num_layers=4, concat_xyz=False, num_classes=13, ratio=0.25, k=16,
+                 prev_grid_size=0.04, sigma=1.0, stem_transformer=False, activation="Relu"):
+        super().__init__()
+        dpr = [x.item() for x in torch.linspace(0, drop_path_rate, sum(depths))]
+        c_in = 6 if concat_xyz else 3
+        if stem_transformer:
+            self.stem_layer = nn.ModuleList([KPConvSimpleBlock(c_in, channels[0], prev_grid_size, sigma=sigma)])
+            self.layer_start = 0
+        else:
+            self.stem_layer = nn.ModuleList([KPConvSimpleBlock(c_in, channels[0], prev_grid_size, sigma=sigma),
+                                             KPConvResBlock(channels[0], channels[0], prev_grid_size, sigma=sigma)])
+            self.downsample = TransitionDown(channels[0], channels[1], ratio, k)
+            self.layer_start = 1
+        self.layers = nn.ModuleList([
+            BasicLayer(downsample_scale, depths[i], channels[i], num_heads[i], window_size[i], grid_sizes[i], quant_sizes[i],
+                       rel_query=rel_query, rel_key=rel_key, rel_value=rel_value, drop_path=dpr[sum(depths[:i]):sum(depths[:i + 1])],
+                       downsample=TransitionDown if i < num_layers - 1 else None, ratio=ratio, k=k,
+                       out_channels=channels[i + 1] if i < num_layers - 1 else None)
+            for i in range(self.layer_start, num_layers)])
+        self.upsamples = nn.ModuleList([Upsample(up_k, channels[i], channels[i - 1]) for i in range(num_layers - 1, 0, -1)])
+        self.classifier = nn.Sequential(nn.Linear(channels[0], channels[0]), nn.BatchNorm1d(channels[0]), nn.ReLU(inplace=True),
+                                        nn.Linear(channels[0], num_classes))
+        act_reg = nn.Tanh() if activation == "Tanh" else nn.ReLU(inplace=True)
+        self.regressor = nn.Sequential(nn.Linear(channels[0], channels[0]), nn.BatchNorm1d(channels[0]), act_reg,
+                                       nn.Linear(channels[0], 3))
+        self.init_weights()
+
+    def forward(self, feats, xyz, offset, batch, neighbor_idx):
+        stack = []
+        for layer in self.stem_layer:
+            feats = layer(feats, xyz, batch, neighbor_idx)
+        feats = feats.contiguous()
+        if self.layer_start == 1:
+            stack.append((feats, xyz, offset))
+            feats, xyz, offset = self.downsample(feats, xyz, offset)
+        for layer in self.layers:
+            feats, xyz, offset, feats_down, xyz_down, offset_down = layer(feats, xyz, offset)
+            stack.append((feats, xyz, offset))
+            feats, xyz, offset = feats_down, xyz_down, offset_down
+        feats, xyz, offset = stack.pop()
+        for upsample in self.upsamples:
+            s_feats, s_xyz, s_offset = stack.pop()
+            feats, xyz, offset = upsample(feats, xyz, s_xyz, offset, s_offset, support_feats=s_feats)
+        return self.classifier(feats), self.regressor(feats)
+
+    def init_weights(self):
+        def _init(m):
+            if isinstance(m, nn.Linear):
+                trunc_normal_(m.weight, std=0.02)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+            elif isinstance(m, (nn.LayerNorm, nn.BatchNorm1d)):
+                nn.init.constant_(m.bias, 0)
+                nn.init.constant_(m.weight, 1.0)
+        self.apply(_init)

@@ -216,6 +216,57 @@ def ref_layer_leg(dev, reps=3):
                     "synchronize on both sides, host work (the reference's Python index construction) included"}
 
 
+def ref_model_leg(dev, reps=2):
+    """Whole-network like-for-like baseline ("whole model"): the reference's own `Stratified` (S3DIS configuration, its
+    Python, its autograd functions, its kernels: oracle/_ref/ref_model_native.py) against `stratified_transformer_b200.model.Stratified`,
+    forward + backward on ONE 80k-point scene, same state dict, same inputs (neighbour lists from prestep.ball_query on both sides).
+    torch_points3d's KPConvLayer is this package's torch restatement on both sides; tests/test_gpu_model.py checks the two agree."""
+    import importlib.util
+    path = os.path.join(ROOT, "oracle", "_ref", "ref_model_native.py")
+    if not (os.path.exists(path) and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libpointops2_ref.so"))):
+        return {"unavailable": "oracle/_ref/ref_model_native.py / libpointops2_ref.so not built (needs /root/reference at build time)"}
+    spec = importlib.util.spec_from_file_location("ref_model_native", path)
+    nat = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(nat)
+    from stratified_transformer_b200 import prestep
+    from stratified_transformer_b200.model import Stratified
+    from stratified_transformer_b200.synthetic import make_batch
+    xyz, rgb, offset = make_batch(1, 80000, seed0=7)
+    xd, od = torch.from_numpy(xyz).to(dev), torch.from_numpy(offset).to(dev)
+    feat = torch.cat([torch.from_numpy(rgb).to(dev).float(), xd], 1)
+    batch = prestep.batch_from_offset(od)
+    nbr = prestep.ball_query(2.5 * 0.04, 34, xd, xd, mode="partial_dense", batch_x=batch, batch_y=batch)[0]
+    cfg = dict(downsample_scale=DS_SCALE, depths=[c["depth"] for c in LAYERS], channels=[c["C"] for c in LAYERS],
+               num_heads=[c["h"] for c in LAYERS], window_size=[c["window"] for c in LAYERS], up_k=3,
+               grid_sizes=[0.04 * 2 ** i for i in range(len(LAYERS))], quant_sizes=[c["quant"] for c in LAYERS], rel_query=True,
+               rel_key=True, rel_value=True, drop_path_rate=0.0, num_layers=len(LAYERS), concat_xyz=True, num_classes=13, ratio=0.25,
+               k=16, prev_grid_size=0.04, sigma=1.0, stem_transformer=True)
+    torch.manual_seed(0)
+    theirs = nat.Stratified(**cfg).to(dev)
+    mine = Stratified(**cfg).to(dev)
+    mine.load_state_dict(theirs.state_dict())
+
+    def step(model):
+        model.zero_grad(set_to_none=True)
+        out, shift = model(feat, xd, od, batch, nbr)
+        (out.square().mean() + shift.square().mean()).backward()
+
+    def timed(model, n):
+        step(model)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            step(model)
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / n * 1e3
+    ref_ms, ours_ms = timed(theirs, reps), timed(mine, max(reps, 5))
+    return {"workload": "whole Stratified network (S3DIS configuration of cfg2: depths 2/2/6/2, channels 48..384, stem_transformer as in "
+                        "config/s3dis/s3dis_stratified_transformer.yaml) fwd+bwd, 1 synthetic 80k-pt scene",
+            "ref_ms": round(ref_ms, 2), "ours_ms": round(ours_ms, 2), "speedup": round(ref_ms / ours_ms, 2),
+            "points_per_s_ours": round(xd.shape[0] / (ours_ms * 1e-3)), "points_per_s_ref": round(xd.shape[0] / (ref_ms * 1e-3)),
+            "note": "wall clock with a device synchronize on both sides; the KPConv stem is the same torch restatement on both sides"}
+
+
 def ref_cuda_leg(dev, reps=10):
     """The >= 10x target's denominator, measured in the same run (SURVEY 8d "Reference-GPU baseline"): the REFERENCE's own
     kernels (oracle/_ref = lib/pointops2/src/{attention_v2,rpe_v2}/*.cu compiled in place, unmodified launchers
@@ -908,6 +959,10 @@ def main():
             ref_cuda_baseline["layer"] = ref_layer_leg(dev)
         except Exception as exc:
             ref_cuda_baseline["layer"] = {"error": f"{type(exc).__name__}: {exc}"}
+        try:
+            ref_cuda_baseline["model"] = ref_model_leg(dev)
+        except Exception as exc:
+            ref_cuda_baseline["model"] = {"error": f"{type(exc).__name__}: {exc}"}
         torch.cuda.empty_cache()
 
     line = {

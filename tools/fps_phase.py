@@ -6,7 +6,7 @@ from stratified_transformer_b200 import pointops, _cabi
 lib = _cabi.load()
 lib.stb200_fps_debug_buffer.argtypes = [ctypes.c_void_p]
 lib.stb200_fps_debug_buffer.restype = None
-b, n = 8, int(sys.argv[1]) if len(sys.argv) > 1 else 80000
+b, n = int(os.environ.get("FPS_PHASE_SCENES", "8")), int(sys.argv[1]) if len(sys.argv) > 1 else 80000
 first = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 lib.stb200_fps_debug_window.argtypes = [ctypes.c_int]
 lib.stb200_fps_debug_window.restype = None

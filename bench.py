@@ -141,7 +141,8 @@ def run_reference_arm(a):
     n = a.cpu_sample_points or (40000 if total <= 25 else max(16000, int(40000 * 25 / total) // 1000 * 1000))
     cores = os.cpu_count()
     pps, dt = cpu_hot_path(n, a.steps, a.warmup)
-    size_note = "BASELINE configs[0] size" if n == 40000 else f"configs[0] is 40000 points; reduced because {total} passes were requested"
+    size_note = "BASELINE configs[0] size" if n == 40000 else (
+        "--cpu-sample-points" if a.cpu_sample_points else f"configs[0] is 40000 points; reduced because {total} passes were requested")
     sample = f"1 synthetic S3DIS-shape scene of {n} points ({size_note}), full 4-layer / 12-block schedule fwd+bwd, fp32, torch CPU {cores} threads"
     line = {
         "metric": METRIC, "value": pps, "unit": "points/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,

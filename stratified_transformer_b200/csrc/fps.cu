@@ -791,7 +791,9 @@ static int fps_run(int b, int n, const float *xyz, const int *offset, const int 
     const int logB = ref_block_log2(n);
     // cluster size: as many CTAs per scene as keep all scenes co-resident (148 SMs), but never more threads than points
     // tuning overrides (development): STB200_FPS_CLUSTER caps the cluster size, STB200_FPS_THREADS sets the CTA size
-    const int threads = env_int("STB200_FPS_THREADS", kFpsThreads);
+    // one or two large scenes get 16 CTAs each either way; 128-thread CTAs (40 points per thread) then measured 4.6 % faster than
+    // 256-thread ones (fewer warps in the CTA-level argmax): 15.3 vs 16.1 ms for 20 001 samples of one 80k-point scene
+    const int threads = env_int("STB200_FPS_THREADS", (b <= 2 && n >= 65536) ? 128 : kFpsThreads);
     // target points per thread when choosing the cluster size: small scenes spread over more CTAs (measured)
     const int per_thread = env_int("STB200_FPS_POINTS", n > 8192 ? 10 : 3);
     int cs = 1;

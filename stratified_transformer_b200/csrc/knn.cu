@@ -18,6 +18,8 @@
 // cells goes on a list that the exact heap kernel above processes afterwards.
 #include "common.cuh"
 
+#include <cstdlib>
+
 #include <cub/cub.cuh>
 
 namespace stb200 {
@@ -111,8 +113,11 @@ __global__ void __launch_bounds__(kKnnThreads) knn_kernel(int m, int b, int k, c
 
 // ---- grid-pruned search --------------------------------------------------------------------------------------------------
 struct KnnBox { float mnx, mny, mnz, cell, inv_cell; int n, start, pad; };
+constexpr int kKnnMaxScenes = 256;
+constexpr int kKnnRowDim = 260;   // cells per axis are capped at 256 (+1 shift, +1 for the neighbour of the last cell): row table [260][260]
 
-__global__ void knn_scene_box_kernel(int b, const float *__restrict__ xyz, const int *__restrict__ offset, KnnBox *__restrict__ box) {
+__global__ void knn_scene_box_kernel(int b, const float *__restrict__ xyz, const int *__restrict__ offset, KnnBox *__restrict__ box,
+                                     float pts_per_cell) {
     __shared__ float red[6][32];
     const int s = blockIdx.x;
     const int start = s ? offset[s - 1] : 0, n = offset[s] - start;
@@ -142,10 +147,10 @@ __global__ void knn_scene_box_kernel(int b, const float *__restrict__ xyz, const
         KnnBox bx;
         bx.mnx = red[0][0]; bx.mny = red[1][0]; bx.mnz = red[2][0];
         const float ex = fmaxf(red[3][0] - red[0][0], 1e-6f), ey = fmaxf(red[4][0] - red[1][0], 1e-6f), ez = fmaxf(red[5][0] - red[2][0], 1e-6f);
-        // cell edge: the cube that would hold 8 points at uniform density, but at least extent / 1000 so that the cell
-        // coordinates stay far below 2^16; scans and indoor rooms are surfaces, the ring expansion covers what this under-estimates
-        float cell = cbrtf(ex * ey * ez * 8.f / (float)max(n, 1));
-        cell = fmaxf(cell, fmaxf(ex, fmaxf(ey, ez)) * 1e-3f);
+        // cell edge: the cube that would hold 2 points at uniform density (measured best of 8 / 2 / 0.5 on room scenes: dense clutter makes
+        // large cells expensive for the queries next to it), but at least extent / 255; scans and indoor rooms are surfaces, the ring expansion covers what this under-estimates
+        float cell = cbrtf(ex * ey * ez * pts_per_cell / (float)max(n, 1));
+        cell = fmaxf(cell, fmaxf(ex, fmaxf(ey, ez)) / 255.f);   // at most 256 cells per axis: the (z, y) row table stays small
         bx.cell = cell; bx.inv_cell = 1.0f / cell; bx.n = n; bx.start = start; bx.pad = 0;
         box[s] = bx;
     }
@@ -185,13 +190,25 @@ __global__ void knn_gather_kernel(int N, const float *__restrict__ xyz, const in
     }
 }
 
+// first / one-past-last sorted position of every (scene, z, y) row of cells: a query finds its 9 rows with two loads each
+// instead of a binary search over all keys (which cost 9 x 17 dependent global loads per query)
+__global__ void knn_rows_kernel(int N, const unsigned long long *__restrict__ keys, int *__restrict__ row_start, int *__restrict__ row_end) {
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) {
+        const unsigned long long r = __ldg(keys + j) >> 16;
+        const int scene = (int)(r >> 32), z = (int)((r >> 16) & 0xffff), y = (int)(r & 0xffff);
+        const size_t slot = ((size_t)scene * kKnnRowDim + min(z, kKnnRowDim - 1)) * kKnnRowDim + min(y, kKnnRowDim - 1);
+        if (j == 0 || (__ldg(keys + j - 1) >> 16) != r) row_start[slot] = j;
+        if (j == N - 1 || (__ldg(keys + j + 1) >> 16) != r) row_end[slot] = j + 1;
+    }
+}
+
 constexpr int kKnnGridMaxK = 32;     // the grid search keeps k + 1 candidates in registers / local memory; larger k: heap kernel
 constexpr int kKnnMaxRing = 4;
 
 __global__ void __launch_bounds__(128)
 knn_grid_kernel(int m, int b, int k, int N, const float *__restrict__ new_xyz, const int *__restrict__ new_offset,
                 const KnnBox *__restrict__ box, const unsigned long long *__restrict__ keys, const float4 *__restrict__ pts,
-                int *__restrict__ idx, float *__restrict__ dist2, int *__restrict__ qlist, int *__restrict__ qcount) {
+                const int *__restrict__ row_start, const int *__restrict__ row_end, int *__restrict__ idx, float *__restrict__ dist2, int *__restrict__ qlist, int *__restrict__ qcount) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= m) return;
     const int s = knn_scene_of(q, b, new_offset);
@@ -208,14 +225,17 @@ knn_grid_kernel(int m, int b, int k, int N, const float *__restrict__ new_xyz, c
             for (int dz = -r; dz <= r; ++dz)
                 for (int dy = -r; dy <= r; ++dy) {
                     const int z = cz + dz, y = cy + dy;
-                    if (z < 0 || y < 0 || z > 65535 || y > 65535) continue;
+                    if (z < 0 || y < 0 || z >= kKnnRowDim || y >= kKnnRowDim) continue;
                     const unsigned long long k_lo = knn_key(s, z, y, max(cx - r, 0)), k_hi = knn_key(s, z, y, min(cx + r, 65535));
-                    int lo = 0, hi = N;
-                    while (lo < hi) {
+                    const size_t slot = ((size_t)s * kKnnRowDim + z) * kKnnRowDim + y;
+                    int lo = __ldg(row_start + slot), hi = __ldg(row_end + slot);
+                    const int row_hi = hi;
+                    while (hi - lo > 8) {   // lower bound of the x range inside the row (rows are short: a few probes)
                         const int mid = (lo + hi) >> 1;
                         if (__ldg(keys + mid) < k_lo) lo = mid + 1; else hi = mid;
                     }
-                    for (int j = lo; j < N && __ldg(keys + j) <= k_hi; ++j) {
+                    for (int j = lo; j < row_hi && __ldg(keys + j) <= k_hi; ++j) {
+                        if (__ldg(keys + j) < k_lo) continue;
                         const float4 c = __ldg(pts + j);
                         const float ex = __fsub_rn(qx, c.x), ey = __fsub_rn(qy, c.y), ez = __fsub_rn(qz, c.z);
                         const float d = __fmaf_rn(ez, ez, __fmaf_rn(ex, ex, __fmul_rn(ey, ey)));
@@ -250,7 +270,7 @@ knn_grid_kernel(int m, int b, int k, int N, const float *__restrict__ new_xyz, c
 struct KnnScratch {
     KnnBox *box;
     unsigned long long *keys_in, *keys_out;
-    int *vals_in, *vals_out, *qlist, *qcount;
+    int *vals_in, *vals_out, *qlist, *qcount, *row_start, *row_end;
     float4 *pts;
     void *cub_tmp;
     size_t cub_bytes, total;
@@ -269,6 +289,9 @@ static KnnScratch knn_layout(int N, int m, int b, void *base) {
     st.pts = (float4 *)take((size_t)N * 16);
     st.qlist = (int *)take((size_t)m * 4);
     st.qcount = (int *)take(16);
+    const size_t table = b <= kKnnMaxScenes ? (size_t)b * kKnnRowDim * kKnnRowDim * 4 : 0;   // more scenes: heap kernel, no tables
+    st.row_start = (int *)take(table);
+    st.row_end = (int *)take(table);
     st.cub_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, st.cub_bytes, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
                                     (const int *)nullptr, (int *)nullptr, N, 0, 64);
@@ -301,14 +324,15 @@ extern "C" int stb200_knnquery_ws(int n, int m, int b, int nsample, const float 
     STB200_REQUIRE(n >= 0 && m >= 0 && b > 0 && nsample > 0 && nsample <= kKnnMaxK, STB200_ERR_ARG, "bad sizes (nsample <= %d)", kKnnMaxK);
     if (m == 0) return STB200_OK;
     STB200_REQUIRE(xyz && new_xyz && offset && new_offset && idx && dist2, STB200_ERR_ARG, "null pointer");
-    if (nsample > kKnnGridMaxK || n == 0 || b > 65535 || !workspace)   // outside the grid search's range: the heap kernel alone
+    if (nsample > kKnnGridMaxK || n == 0 || b > kKnnMaxScenes || !workspace)   // outside the grid search's range: the heap kernel alone
         return stb200_knnquery(m, b, nsample, xyz, new_xyz, offset, new_offset, idx, dist2, stream);
     KnnScratch st = knn_layout(n, m, b, workspace);
     STB200_REQUIRE(workspace_bytes >= st.total, STB200_ERR_WORKSPACE, "knnquery workspace: %zu B given, %zu B needed", workspace_bytes, st.total);
     cudaStream_t s = (cudaStream_t)stream;
     {
         KernelScope ks("knnquery_grid_build", 0.0, s);
-        knn_scene_box_kernel<<<b, 256, 0, s>>>(b, xyz, offset, st.box);
+        static const float pts_per_cell = getenv("STB200_KNN_CELL_POINTS") ? (float)atof(getenv("STB200_KNN_CELL_POINTS")) : 2.f;
+        knn_scene_box_kernel<<<b, 256, 0, s>>>(b, xyz, offset, st.box, pts_per_cell);
         knn_keys_kernel<<<min((n + 255) / 256, kNumSMs * 8), 256, 0, s>>>(n, b, xyz, offset, st.box, st.keys_in, st.vals_in);
         size_t tb = st.cub_bytes;
         cudaError_t e = cub::DeviceRadixSort::SortPairs(st.cub_tmp, tb, st.keys_in, st.keys_out, st.vals_in, st.vals_out, n, 0, 64, s);
@@ -316,11 +340,14 @@ extern "C" int stb200_knnquery_ws(int n, int m, int b, int nsample, const float 
         knn_gather_kernel<<<min((n + 255) / 256, kNumSMs * 8), 256, 0, s>>>(n, xyz, st.vals_out, st.pts);
         e = cudaMemsetAsync(st.qcount, 0, sizeof(int), s);
         STB200_REQUIRE(e == cudaSuccess, STB200_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
+        e = cudaMemsetAsync(st.row_start, 0, (size_t)((char *)st.row_end - (char *)st.row_start) * 2, s);   // the two tables are adjacent
+        STB200_REQUIRE(e == cudaSuccess, STB200_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
+        knn_rows_kernel<<<min((n + 255) / 256, kNumSMs * 8), 256, 0, s>>>(n, st.keys_out, st.row_start, st.row_end);
     }
     {
         KernelScope ks("knnquery_grid", 0.0, s);
-        knn_grid_kernel<<<(m + 127) / 128, 128, 0, s>>>(m, b, nsample, n, new_xyz, new_offset, st.box, st.keys_out, st.pts, idx, dist2,
-                                                       st.qlist, st.qcount);
+        knn_grid_kernel<<<(m + 127) / 128, 128, 0, s>>>(m, b, nsample, n, new_xyz, new_offset, st.box, st.keys_out, st.pts, st.row_start, st.row_end, idx,
+                                                       dist2, st.qlist, st.qcount);
     }
     {   // the queries the grid could not settle (ties, sparse neighbourhoods, tiny scenes): exact heap scan; idle CTAs exit at once
         KernelScope ks("knnquery", 0.0, s);

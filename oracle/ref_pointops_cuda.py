@@ -8,8 +8,6 @@ The launchers use the legacy default stream, which is torch's default stream: no
 Only the entry points the model's layers reach are bound."""
 import ctypes
 
-import torch
-
 from . import ref_cuda
 
 

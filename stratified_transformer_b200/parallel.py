@@ -9,7 +9,7 @@ to a step and therefore left to NCCL over NVLink/NVSwitch rather than a fused ke
 """
 from __future__ import annotations
 
-from typing import Iterable, List, Sequence
+from typing import List, Sequence
 
 import torch
 import torch.distributed as dist

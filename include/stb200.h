@@ -44,7 +44,7 @@ const char *stb200_last_error(void);
 /* number of kernels this library launched since load (bench.py's "gpu_launches") */
 long long stb200_launch_count(void);
 /* ABI version: 100 = first release, 101 = stb200_index has len_order / t_len_order (append-only struct growth),
- * 102 = fused work plan + fused window attention entry points; 103 = stb200_qkv_split / _merge, pre-step (batch vector, ball query) */
+ * 102 = fused work plan + fused window attention entry points; 103 = stb200_qkv_split / _merge, layer norm, pre-step (batch vector, ball query), *_ws variants of FPS / kNN */
 int stb200_version(void);
 /* Optional per-kernel profiler: when enabled every launch is bracketed by CUDA events on its stream.
  * stb200_profile_dump writes a JSON object {"kernel name": {"launches", "ms", "bytes"}} (bytes = algorithmic bytes
@@ -340,6 +340,16 @@ int stb200_qkv_partial_rows(int N, int C);
 int stb200_qkv_split(int N, int C, int dtype, const void *qkv, const float *bias, float *q, float *k, float *v, void *stream);
 int stb200_qkv_merge(int N, int C, int dtype, const float *grad_q, const float *grad_k, const float *grad_v, void *grad_qkv,
                      float *bias_partial, void *stream);
+
+/* nn.LayerNorm(C) over the last dimension of fp32 [N, C], 1 <= C <= 384 (model/stratified_transformer.py:227,233 and the norms of
+ * TransitionDown / Upsample): y = (x - mean) * rstd * gamma + beta, biased variance, rstd = rsqrt(var + eps); mean / rstd [N] are kept
+ * for the backward pass.  Backward: grad_x, and per-CTA partial sums partial [stb200_layer_norm_partial_rows(N, C), 2C] whose sum over
+ * rows is (grad_gamma | grad_beta) (NULL: not wanted).  gamma / beta may be NULL (no affine part). */
+int stb200_layer_norm_partial_rows(long long N, int C);
+int stb200_layer_norm_forward(long long N, int C, float eps, const float *x, const float *gamma, const float *beta, float *y, float *mean,
+                              float *rstd, void *stream);
+int stb200_layer_norm_backward(long long N, int C, const float *grad_y, const float *x, const float *gamma, const float *mean,
+                               const float *rstd, float *grad_x, float *partial, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Host pre-step of the training loop on the device — replaces train.py:319-325.

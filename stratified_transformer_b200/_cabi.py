@@ -81,6 +81,8 @@ _SIGNATURES = {
     "stb200_tc_selftest": [_c_int] * 4 + [P] * 5,
     "stb200_qkv_split": [_c_int] * 3 + [P] * 6,
     "stb200_qkv_merge": [_c_int] * 3 + [P] * 6,
+    "stb200_layer_norm_forward": [ctypes.c_longlong, _c_int, ctypes.c_float] + [P] * 7,
+    "stb200_layer_norm_backward": [ctypes.c_longlong, _c_int] + [P] * 8,
     "stb200_batch_from_offset": [_c_int, _c_int, P, P, P],
     "stb200_ball_query": [_c_int, _c_int, ctypes.c_float, _c_int, P, P, P, P, P, _c_size_t, P, P, P],
     "stb200_set_torch_semantics": [_c_int],
@@ -97,6 +99,7 @@ _RESTYPES = {
     "stb200_fused_max_keys": (_c_int, []),
     "stb200_fused_plan_scratch_bytes": (_c_size_t, [_c_int]),
     "stb200_qkv_partial_rows": (_c_int, [_c_int, _c_int]),
+    "stb200_layer_norm_partial_rows": (_c_int, [ctypes.c_longlong, _c_int]),
     "stb200_ball_query_workspace_bytes": (_c_size_t, [_c_int]),
     "stb200_knnquery_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
     "stb200_fps_workspace_bytes": (_c_size_t, [_c_int, _c_int]),

@@ -121,6 +121,136 @@ static int qkv_grid(int N, int rows_per_step) {
     return (int)(need < cap ? (need < 1 ? 1 : need) : cap);
 }
 
+
+// ---- LayerNorm over short rows -------------------------------------------------------------------------------------------
+// nn.LayerNorm(C) on [N, C] with C = 48 ... 384 is what every block of the model runs twice (SwinTransformerBlock.norm1 / norm2,
+// model/stratified_transformer.py:227,233) plus TransitionDown / Upsample; torch's kernel gives a whole warp (or more) to each
+// 48-float row and reaches ~0.6 TB/s forward, less backward (12.8 + 15.3 ms per step of the full model on 8 x 80k points).
+// Here a group of G = 8 / 16 / 32 lanes owns a row (at most 12 elements per lane, kept in registers), statistics by shuffles
+// inside the group, and the backward pass accumulates the gamma / beta gradients of its columns in registers across all the
+// rows a thread sees, reduces them through shared memory once per CTA and writes per-CTA partials (deterministic).
+constexpr int kLnThreads = 256;
+constexpr int kLnMaxPer = 12;   // elements per lane
+
+template <int G>
+__device__ __forceinline__ float group_sum_ln(float v) {
+#pragma unroll
+    for (int o = G / 2; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int G>
+__global__ void __launch_bounds__(kLnThreads) layer_norm_fwd_kernel(long long N, int C, float eps, const float *__restrict__ x,
+                                                                    const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                                    float *__restrict__ y, float *__restrict__ mean, float *__restrict__ rstd) {
+    const int lane = threadIdx.x % G, grp = threadIdx.x / G, groups = kLnThreads / G;
+    const int per = (C + G - 1) / G;
+    float gm[kLnMaxPer], bt[kLnMaxPer];
+#pragma unroll
+    for (int t = 0; t < kLnMaxPer; ++t) {
+        const int c = lane + t * G;
+        gm[t] = (t < per && c < C && gamma) ? __ldg(gamma + c) : 1.f;
+        bt[t] = (t < per && c < C && beta) ? __ldg(beta + c) : 0.f;
+    }
+    const float inv_c = 1.0f / (float)C;
+    // the row base is CTA-uniform, so every lane of a warp runs the same number of iterations and takes part in the shuffles; rows
+    // past the end are masked (a loop bound per group would leave the full-mask shuffles of the other groups waiting forever)
+    for (long long base = (long long)blockIdx.x * groups; base < N; base += (long long)gridDim.x * groups) {
+        const long long r = base + grp;
+        const bool row_on = r < N;
+        float v[kLnMaxPer];
+        float s = 0.f;
+#pragma unroll
+        for (int t = 0; t < kLnMaxPer; ++t) {
+            const int c = lane + t * G;
+            v[t] = (row_on && t < per && c < C) ? __ldg(x + r * C + c) : 0.f;
+            s += v[t];
+        }
+        const float mu = group_sum_ln<G>(s) * inv_c;
+        float q = 0.f;
+#pragma unroll
+        for (int t = 0; t < kLnMaxPer; ++t) {
+            const int c = lane + t * G;
+            const float d = (t < per && c < C) ? v[t] - mu : 0.f;
+            q = fmaf(d, d, q);
+        }
+        const float rs = rsqrtf(group_sum_ln<G>(q) * inv_c + eps);
+#pragma unroll
+        for (int t = 0; t < kLnMaxPer; ++t) {
+            const int c = lane + t * G;
+            if (row_on && t < per && c < C) y[r * C + c] = fmaf((v[t] - mu) * rs, gm[t], bt[t]);
+        }
+        if (row_on && lane == 0) { mean[r] = mu; rstd[r] = rs; }
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(kLnThreads) layer_norm_bwd_kernel(long long N, int C, const float *__restrict__ g, const float *__restrict__ x,
+                                                                    const float *__restrict__ gamma, const float *__restrict__ mean,
+                                                                    const float *__restrict__ rstd, float *__restrict__ gx,
+                                                                    float *__restrict__ partial /* [grid, 2C]: dgamma | dbeta */) {
+    extern __shared__ float ln_red[];   // [groups][2C]
+    const int lane = threadIdx.x % G, grp = threadIdx.x / G, groups = kLnThreads / G;
+    const int per = (C + G - 1) / G;
+    float gm[kLnMaxPer], dg[kLnMaxPer], db[kLnMaxPer];
+#pragma unroll
+    for (int t = 0; t < kLnMaxPer; ++t) {
+        const int c = lane + t * G;
+        gm[t] = (t < per && c < C && gamma) ? __ldg(gamma + c) : 1.f;
+        dg[t] = 0.f;
+        db[t] = 0.f;
+    }
+    const float inv_c = 1.0f / (float)C;
+    for (long long base = (long long)blockIdx.x * groups; base < N; base += (long long)gridDim.x * groups) {   // uniform, see forward
+        const long long r = base + grp;
+        const bool row_on = r < N;
+        const float mu = row_on ? __ldg(mean + r) : 0.f, rs = row_on ? __ldg(rstd + r) : 0.f;
+        float xh[kLnMaxPer], a[kLnMaxPer];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int t = 0; t < kLnMaxPer; ++t) {
+            const int c = lane + t * G;
+            const bool on = row_on && t < per && c < C;
+            const float gv = on ? __ldg(g + r * C + c) : 0.f;
+            xh[t] = on ? (__ldg(x + r * C + c) - mu) * rs : 0.f;
+            a[t] = gv * gm[t];
+            s1 += a[t];
+            s2 = fmaf(a[t], xh[t], s2);
+            dg[t] = fmaf(gv, xh[t], dg[t]);
+            db[t] += gv;
+        }
+        s1 = group_sum_ln<G>(s1) * inv_c;
+        s2 = group_sum_ln<G>(s2) * inv_c;
+#pragma unroll
+        for (int t = 0; t < kLnMaxPer; ++t) {
+            const int c = lane + t * G;
+            if (row_on && t < per && c < C) gx[r * C + c] = rs * (a[t] - s1 - xh[t] * s2);
+        }
+    }
+    if (!partial) return;
+#pragma unroll
+    for (int t = 0; t < kLnMaxPer; ++t) {
+        const int c = lane + t * G;
+        if (t < per && c < C) {
+            ln_red[(size_t)grp * 2 * C + c] = dg[t];
+            ln_red[(size_t)grp * 2 * C + C + c] = db[t];
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * C; c += kLnThreads) {
+        float s = 0.f;
+        for (int gI = 0; gI < groups; ++gI) s += ln_red[(size_t)gI * 2 * C + c];
+        partial[(size_t)blockIdx.x * 2 * C + c] = s;
+    }
+}
+
+static int ln_group(int C) { return C <= 96 ? (C <= 48 ? 8 : 16) : 32; }   // <= 12 elements per lane up to C = 384
+static int ln_grid(long long N, int G) {
+    const long long need = (N + kLnThreads / G - 1) / (kLnThreads / G);
+    const long long cap = 8LL * kNumSMs;
+    return (int)(need < cap ? (need < 1 ? 1 : need) : cap);
+}
+
 }  // namespace stb200
 
 using namespace stb200;
@@ -161,6 +291,42 @@ int stb200_qkv_merge(int N, int C, int dtype, const float *gq, const float *gk, 
     else if (dtype == 2) qkv_merge_kernel<__half><<<grid, kQkvThreads, 0, s>>>(N, C, gq, gk, gv, (__half *)g_qkv, bias_partial, rps);
     else { set_error("qkv_merge: dtype %d (0 = fp32, 1 = bf16, 2 = fp16)", dtype); return STB200_ERR_ARG; }
     return check_launch("qkv_merge");
+}
+
+}  // extern "C"
+
+extern "C" {
+
+int stb200_layer_norm_partial_rows(long long N, int C) {
+    if (N <= 0 || C <= 0 || C > 32 * kLnMaxPer) return 0;
+    return ln_grid(N, ln_group(C));
+}
+
+int stb200_layer_norm_forward(long long N, int C, float eps, const float *x, const float *gamma, const float *beta, float *y, float *mean,
+                              float *rstd, void *stream) {
+    STB200_REQUIRE(N > 0 && C > 0 && C <= 32 * kLnMaxPer, STB200_ERR_ARG, "layer_norm: C must be in 1..%d (got %d)", 32 * kLnMaxPer, C);
+    STB200_REQUIRE(x && y && mean && rstd, STB200_ERR_ARG, "null pointer");
+    const int G = ln_group(C), grid = ln_grid(N, G);
+    cudaStream_t s = (cudaStream_t)stream;
+    KernelScope ks("layer_norm_fwd", 8.0 * N * C + 8.0 * N, s);
+    if (G == 8) layer_norm_fwd_kernel<8><<<grid, kLnThreads, 0, s>>>(N, C, eps, x, gamma, beta, y, mean, rstd);
+    else if (G == 16) layer_norm_fwd_kernel<16><<<grid, kLnThreads, 0, s>>>(N, C, eps, x, gamma, beta, y, mean, rstd);
+    else layer_norm_fwd_kernel<32><<<grid, kLnThreads, 0, s>>>(N, C, eps, x, gamma, beta, y, mean, rstd);
+    return check_launch("layer_norm_fwd");
+}
+
+int stb200_layer_norm_backward(long long N, int C, const float *grad_y, const float *x, const float *gamma, const float *mean,
+                               const float *rstd, float *grad_x, float *partial, void *stream) {
+    STB200_REQUIRE(N > 0 && C > 0 && C <= 32 * kLnMaxPer, STB200_ERR_ARG, "layer_norm: C must be in 1..%d (got %d)", 32 * kLnMaxPer, C);
+    STB200_REQUIRE(grad_y && x && mean && rstd && grad_x, STB200_ERR_ARG, "null pointer");
+    const int G = ln_group(C), grid = ln_grid(N, G);
+    const size_t smem = (size_t)(kLnThreads / G) * 2 * C * sizeof(float);
+    cudaStream_t s = (cudaStream_t)stream;
+    KernelScope ks("layer_norm_bwd", 12.0 * N * C + 8.0 * N, s);
+    if (G == 8) layer_norm_bwd_kernel<8><<<grid, kLnThreads, smem, s>>>(N, C, grad_y, x, gamma, mean, rstd, grad_x, partial);
+    else if (G == 16) layer_norm_bwd_kernel<16><<<grid, kLnThreads, smem, s>>>(N, C, grad_y, x, gamma, mean, rstd, grad_x, partial);
+    else layer_norm_bwd_kernel<32><<<grid, kLnThreads, smem, s>>>(N, C, grad_y, x, gamma, mean, rstd, grad_x, partial);
+    return check_launch("layer_norm_bwd");
 }
 
 }  // extern "C"

@@ -17,6 +17,16 @@ from . import pointops
 from .window_attention import WindowAttention
 
 
+class LayerNorm(nn.LayerNorm):
+    """nn.LayerNorm with the same parameters; fp32 CUDA inputs normalised over a last dimension of at most 384 elements go through
+    the short-row kernels of libstb200 (torch's kernel spends 28 ms per step of the full model on these 48..384-wide rows)."""
+
+    def forward(self, x):
+        if x.is_cuda and len(self.normalized_shape) == 1 and self.normalized_shape[0] <= 384 and x.dtype in (torch.float32, torch.bfloat16, torch.float16):
+            return pointops.layer_norm(x, self.weight, self.bias, self.eps)
+        return super().forward(x)
+
+
 class DropPath(nn.Module):
     """Stochastic depth per sample (the first dimension), scaled by the keep probability - what the reference imports from
     timm (`timm.models.layers.DropPath`, stratified_transformer.py:5); identity when not training or drop_prob == 0."""
@@ -65,7 +75,7 @@ def transition_down_offsets(offset, ratio):
 class TransitionDown(nn.Module):
     """stratified_transformer.py:87-112: FPS to ratio * n points, kNN grouping, LayerNorm + Linear per neighbour, max pool."""
 
-    def __init__(self, in_channels, out_channels, ratio, k, norm_layer=nn.LayerNorm):
+    def __init__(self, in_channels, out_channels, ratio, k, norm_layer=LayerNorm):
         super().__init__()
         self.ratio = ratio
         self.k = k
@@ -88,7 +98,10 @@ class TransitionDown(nn.Module):
         m, k, c = grouped.shape
         if self.norm is not None:
             grouped = self.norm(grouped)
-        pooled = self.pool(self.linear(grouped).transpose(1, 2).contiguous()).squeeze(-1)                      # (m, c_out)
+        # max over the k neighbours = `self.pool(x.transpose(1, 2).contiguous()).squeeze(-1)` of the reference (line 109) without the
+        # transposed copy; the gradient goes to the arg-max either way (MaxPool1d's backward kernel alone took 10 ms per step of
+        # the full model on 8 x 80k points, this one 1 ms)
+        pooled = self.linear(grouped).max(dim=1).values if k == self.k else self.pool(self.linear(grouped).transpose(1, 2).contiguous()).squeeze(-1)
         return pooled, n_xyz, n_offset
 
 
@@ -100,8 +113,8 @@ class Upsample(nn.Module):
         self.k = k
         self.in_channels = in_channels
         self.out_channels = out_channels
-        self.linear1 = nn.Sequential(nn.LayerNorm(out_channels), nn.Linear(out_channels, out_channels))
-        self.linear2 = nn.Sequential(nn.LayerNorm(in_channels), nn.Linear(in_channels, out_channels))
+        self.linear1 = nn.Sequential(LayerNorm(out_channels), nn.Linear(out_channels, out_channels))
+        self.linear2 = nn.Sequential(LayerNorm(in_channels), nn.Linear(in_channels, out_channels))
 
     def forward(self, feats, xyz, support_xyz, offset, support_offset, support_feats=None):
         up = pointops.interpolation(xyz, support_xyz, self.linear2(feats), offset, support_offset)
@@ -113,7 +126,7 @@ class SwinTransformerBlock(nn.Module):
     forward(feats, xyz, index_0, index_1, index_0_offsets, n_max)."""
 
     def __init__(self, dim, num_heads, window_size, quant_size, rel_query=True, rel_key=False, rel_value=False, drop_path=0.0,
-                 mlp_ratio=4.0, qkv_bias=True, qk_scale=None, act_layer=nn.GELU, norm_layer=nn.LayerNorm, mode=4):
+                 mlp_ratio=4.0, qkv_bias=True, qk_scale=None, act_layer=nn.GELU, norm_layer=LayerNorm, mode=4):
         super().__init__()
         self.mode = mode
         self.norm1 = norm_layer(dim)
@@ -138,7 +151,7 @@ class BasicLayer(nn.Module):
 
     def __init__(self, downsample_scale, depth, channel, num_heads, window_size, grid_size, quant_size, rel_query=True,
                  rel_key=False, rel_value=False, drop_path=0.0, mlp_ratio=4.0, qkv_bias=True, qk_scale=None,
-                 norm_layer=nn.LayerNorm, downsample=None, ratio=0.25, k=16, out_channels=None):
+                 norm_layer=LayerNorm, downsample=None, ratio=0.25, k=16, out_channels=None):
         super().__init__()
         self.depth = depth
         self.grid_size = grid_size

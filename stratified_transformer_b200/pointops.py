@@ -381,6 +381,54 @@ def window_attention_plan(q, k, v, table_q, table_k, table_v, plan):
     return WindowAttentionPlan.apply(q, k, v, table_q, table_k, table_v, plan)
 
 
+class LayerNormShortRows(Function):
+    """F.layer_norm(x, (C,), weight, bias, eps) for fp32 rows of at most 384 elements (include/stb200.h: stb200_layer_norm_*)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, weight, bias, eps):
+        shape = x.shape
+        C = shape[-1]
+        x2 = x.reshape(-1, C).contiguous()
+        N = x2.shape[0]
+        y = torch.empty_like(x2)
+        mean = torch.empty(N, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(N, dtype=torch.float32, device=x.device)
+        if N:
+            _cabi.call("stb200_layer_norm_forward", N, C, float(eps), x2.data_ptr(), None if weight is None else weight.contiguous().data_ptr(),
+                       None if bias is None else bias.contiguous().data_ptr(), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                       torch.cuda.current_stream().cuda_stream)
+        ctx.save_for_backward(x2, weight, mean, rstd)
+        ctx.has_bias = bias is not None
+        ctx.shape = shape
+        return y.view(shape)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, gy):
+        x2, weight, mean, rstd = ctx.saved_tensors
+        N, C = x2.shape
+        gy2 = gy.reshape(-1, C).float().contiguous()
+        gx = torch.empty_like(x2)
+        want_affine = weight is not None and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+        partial = None
+        if N:
+            if want_affine:
+                partial = torch.empty(_cabi.load().stb200_layer_norm_partial_rows(N, C), 2 * C, dtype=torch.float32, device=gx.device)
+            _cabi.call("stb200_layer_norm_backward", N, C, gy2.data_ptr(), x2.data_ptr(), None if weight is None else weight.contiguous().data_ptr(),
+                       mean.data_ptr(), rstd.data_ptr(), gx.data_ptr(), None if partial is None else partial.data_ptr(),
+                       torch.cuda.current_stream().cuda_stream)
+        gw = gb = None
+        if partial is not None:
+            sums = partial.sum(0)
+            gw, gb = sums[:C], (sums[C:] if ctx.has_bias else None)
+        return gx.view(ctx.shape), gw, gb, None
+
+
+def layer_norm(x, weight, bias, eps=1e-5):
+    return LayerNormShortRows.apply(x, weight, bias, eps)
+
+
 _QKV_DTYPES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 
 

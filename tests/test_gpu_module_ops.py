@@ -53,3 +53,41 @@ def test_bias_gradient_is_deterministic():
         (q.sum() + (k * 2).sum() + (v * q.detach()).sum()).backward()
         outs.append(bias.grad.clone())
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+@pytest.mark.parametrize("shape", [(1, 48), (1000, 48), (4097, 96), (777, 192), (300, 384), (50, 16, 48), (33, 7), (64, 100)])
+@pytest.mark.parametrize("affine", [True, False])
+def test_layer_norm_short_rows_matches_torch(shape, affine):
+    from stratified_transformer_b200 import pointops
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(sum(shape))
+    C = shape[-1]
+    x = (torch.randn(*shape, device=dev, generator=g) * 3 + 1).requires_grad_(True)
+    w = (torch.rand(C, device=dev, generator=g) + 0.5).requires_grad_(True) if affine else None
+    b = torch.randn(C, device=dev, generator=g).requires_grad_(True) if affine else None
+    gy = torch.randn(*shape, device=dev, generator=g)
+    y = pointops.layer_norm(x, w, b, 1e-5)
+    y.backward(gy)
+    got = [y.detach(), x.grad.clone()] + ([w.grad.clone(), b.grad.clone()] if affine else [])
+    x64 = x.detach().double().requires_grad_(True)
+    w64 = w.detach().double().requires_grad_(True) if affine else None
+    b64 = b.detach().double().requires_grad_(True) if affine else None
+    y64 = torch.nn.functional.layer_norm(x64, (C,), w64, b64, 1e-5)
+    y64.backward(gy.double())
+    want = [y64.detach(), x64.grad] + ([w64.grad, b64.grad] if affine else [])
+    for a, r, name in zip(got, want, ("y", "gx", "gw", "gb")):
+        scale = max(1.0, float(r.abs().max()))
+        assert float((a.double() - r).abs().max()) <= 2e-5 * scale, name
+
+
+def test_layer_norm_module_is_a_drop_in_under_autocast():
+    from stratified_transformer_b200.layers import LayerNorm
+    ref = torch.nn.LayerNorm(96).cuda()
+    mine = LayerNorm(96).cuda()
+    mine.load_state_dict(ref.state_dict())
+    x = torch.randn(5000, 96, device="cuda")
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        a, b = mine(x.bfloat16()), ref(x.bfloat16())
+    assert a.dtype == b.dtype == torch.float32
+    assert torch.allclose(a, b, atol=2e-5, rtol=1e-5)
+    assert isinstance(mine, torch.nn.LayerNorm)

@@ -9,7 +9,8 @@ from stratified_transformer_b200.synthetic import make_batch
 from torch.profiler import profile, ProfilerActivity
 
 dev = torch.device("cuda")
-xyz, rgb, offset = make_batch(1, 80000, seed0=7)
+scenes = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+xyz, rgb, offset = make_batch(scenes, 80000, seed0=7)
 xd, od = torch.from_numpy(xyz).to(dev), torch.from_numpy(offset).to(dev)
 feat = torch.cat([torch.from_numpy(rgb).to(dev).float(), xd], 1)
 batch = prestep.batch_from_offset(od)
@@ -20,10 +21,14 @@ model = Stratified(8, [c["depth"] for c in L], [c["C"] for c in L], [c["h"] for 
                    drop_path_rate=0.0, concat_xyz=True, stem_transformer=True).to(dev)
 
 
+amp = len(sys.argv) > 2 and sys.argv[2] == "amp"
+
+
 def step():
     model.zero_grad(set_to_none=True)
-    out, shift = model(feat, xd, od, batch, nbr)
-    (out.square().mean() + shift.square().mean()).backward()
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+        out, shift = model(feat, xd, od, batch, nbr)
+    (out.float().square().mean() + shift.float().square().mean()).backward()
 
 
 for _ in range(2):

@@ -375,7 +375,7 @@ def build_layer_index(xyz: torch.Tensor, offset: torch.Tensor, window_size: floa
 # an event that has usually fired long ago, then enqueues the fill / transposed CSR / packing kernels.
 class PendingLayerIndex:
     def __init__(self, xyz, offset, window_size, quant_size, downsample_scale, offset_host, want_index_0=False, L=None,
-                 fused=False, csr=True):
+                 fused=False, csr=True, downsample_idx=None):
         self.xyz, self.window_size, self.quant_size, self.want_index_0, self.L = xyz, window_size, quant_size, want_index_0, L
         self.fused, self.csr = fused, csr or not fused
         dev = xyz.device
@@ -383,9 +383,9 @@ class PendingLayerIndex:
         self.N = N
         offset = offset.to(device=dev, dtype=torch.int32).contiguous()
         lib = _cabi.load()
-        self.ds_idx = None
-        m = 0
-        if downsample_scale is not None:
+        self.ds_idx = downsample_idx          # FPS picks the caller already has (index.fps_prefix), else sampled here
+        m = 0 if downsample_idx is None else int(downsample_idx.shape[0])
+        if downsample_scale is not None and downsample_idx is None:
             sizes = [int(offset_host[0])] + [int(offset_host[i] - offset_host[i - 1]) for i in range(1, b)]
             new_counts = [n // downsample_scale + 1 for n in sizes]
             m = sum(new_counts)

@@ -167,8 +167,9 @@ class BasicLayer(nn.Module):
             for i in range(depth)])
         self.downsample = downsample(channel, out_channels, ratio, k) if downsample else None
 
-    def forward(self, feats, xyz, offset, layer_index=None):
-        li, fps = layer_index, None
+    def forward(self, feats, xyz, offset, layer_index=None, fps=None):
+        """fps = (idx, n_offset): TransitionDown's furthest-point picks when the caller computed them together with `layer_index`"""
+        li = layer_index
         if li is None:
             ds_idx = None
             if isinstance(self.downsample, TransitionDown) and self.downsample_scale is not None:

@@ -351,6 +351,15 @@ int stb200_layer_norm_forward(long long N, int C, float eps, const float *x, con
 int stb200_layer_norm_backward(long long N, int C, const float *grad_y, const float *x, const float *gamma, const float *mean,
                                const float *rstd, float *grad_x, float *partial, void *stream);
 
+/* Neighbourhood aggregation of the KPConv stem (torch_points3d KPConvLayer: rigid, linear influence, sum; third party, outside the
+ * hot path): weighted[i, k, :] = sum_j max(0, 1 - |s_xyz[nbr[i,j]] - q_xyz[i] - kpts[k]| / extent) * feats[nbr[i,j], :], nbr int64
+ * [n, nn] with entries < 0 or >= n_sup meaning "no neighbour"; K <= 16 kernel points, C <= 16 channels.  The projection
+ * out = sum_k weighted[:, k, :] W_k stays a library GEMM.  Backward accumulates into grad_feats [n_sup, C] (zero it first). */
+int stb200_kpconv_weighted(int n, int n_sup, int nn, int K, int C, float extent, const float *q_xyz, const float *s_xyz,
+                           const long long *nbr, const float *kpts, const float *feats, float *weighted, void *stream);
+int stb200_kpconv_weighted_backward(int n, int n_sup, int nn, int K, int C, float extent, const float *q_xyz, const float *s_xyz,
+                                    const long long *nbr, const float *kpts, const float *grad_weighted, float *grad_feats, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Host pre-step of the training loop on the device — replaces train.py:319-325.
  * stb200_batch_from_offset: batch[i] = scene of point i (the reference builds it with a Python list per scene); offset = cumulative

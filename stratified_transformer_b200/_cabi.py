@@ -83,6 +83,8 @@ _SIGNATURES = {
     "stb200_qkv_merge": [_c_int] * 3 + [P] * 6,
     "stb200_layer_norm_forward": [ctypes.c_longlong, _c_int, ctypes.c_float] + [P] * 7,
     "stb200_layer_norm_backward": [ctypes.c_longlong, _c_int] + [P] * 8,
+    "stb200_kpconv_weighted": [_c_int] * 5 + [ctypes.c_float] + [P] * 7,
+    "stb200_kpconv_weighted_backward": [_c_int] * 5 + [ctypes.c_float] + [P] * 7,
     "stb200_batch_from_offset": [_c_int, _c_int, P, P, P],
     "stb200_ball_query": [_c_int, _c_int, ctypes.c_float, _c_int, P, P, P, P, P, _c_size_t, P, P, P],
     "stb200_set_torch_semantics": [_c_int],

@@ -251,6 +251,66 @@ static int ln_grid(long long N, int G) {
     return (int)(need < cap ? (need < 1 ? 1 : need) : cap);
 }
 
+
+// ---- KPConv neighbourhood aggregation (stem, outside the hot path) ---------------------------------------------------------
+// Rigid kernel-point convolution, linear influence, sum aggregation (torch_points3d KPConvLayer, third party: DESIGN.md section 4):
+//     weighted[i, k, :] = sum_j max(0, 1 - |x_{n(i,j)} - x_i - K_k| / extent) * f[n(i,j), :]          (this kernel)
+//     out[i, :]         = sum_k weighted[i, k, :] W_k                                                  (one GEMM, library)
+// As torch operators the first line materialises [n, 34, 15, 3] differences and [n, 34, 15] weights (several GB at 640k points)
+// forward and backward.  Here a warp takes a query point: lane = neighbour slot (34 slots: two rounds), each lane computes its
+// neighbour's 15 influences, and the [15, C] sums are reduced over the lanes with shuffles.  Neighbour index < 0 or >= n_support
+// is the radius search's padding: no contribution.  Backward scatters grad_f with vector-free float atomics (order-dependent sums
+// in the last bits; the stem is not a parity surface).
+constexpr int kKpMaxK = 16;   // kernel points
+constexpr int kKpMaxC = 16;   // input channels handled by this kernel (the stem has 6 and 12)
+
+template <bool BWD>
+__global__ void __launch_bounds__(256) kpconv_weighted_kernel(int n, int n_sup, int nn, int K, int C, float inv_extent,
+                                                              const float *__restrict__ q_xyz, const float *__restrict__ s_xyz,
+                                                              const long long *__restrict__ nbr, const float *__restrict__ kpts,
+                                                              const float *__restrict__ feats, float *__restrict__ weighted,
+                                                              const float *__restrict__ g_weighted, float *__restrict__ g_feats) {
+    __shared__ float skp[kKpMaxK * 3];
+    if (threadIdx.x < K * 3) skp[threadIdx.x] = kpts[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x % 32, wpb = blockDim.x / 32;
+    for (long long i = (long long)blockIdx.x * wpb + threadIdx.x / 32; i < n; i += (long long)gridDim.x * wpb) {   // warp-uniform
+        const float qx = __ldg(q_xyz + i * 3), qy = __ldg(q_xyz + i * 3 + 1), qz = __ldg(q_xyz + i * 3 + 2);
+        float acc[BWD ? 1 : kKpMaxC];   // forward: this lane's share of one kernel point's [C] sum, reduced below
+        for (int k = 0; k < K; ++k) {
+            if (!BWD)
+#pragma unroll
+                for (int c = 0; c < kKpMaxC; ++c) acc[c] = 0.f;
+            for (int j = lane; j < nn; j += 32) {
+                const long long p = __ldg(nbr + i * nn + j);
+                if (p < 0 || p >= n_sup) continue;
+                const float dx = __ldg(s_xyz + p * 3) - qx - skp[k * 3], dy = __ldg(s_xyz + p * 3 + 1) - qy - skp[k * 3 + 1],
+                            dz = __ldg(s_xyz + p * 3 + 2) - qz - skp[k * 3 + 2];
+                const float w = fmaxf(1.f - sqrtf(dx * dx + dy * dy + dz * dz) * inv_extent, 0.f);
+                if (w == 0.f) continue;
+                if (!BWD) {
+#pragma unroll
+                    for (int c = 0; c < kKpMaxC; ++c)
+                        if (c < C) acc[c] = fmaf(w, __ldg(feats + p * C + c), acc[c]);
+                } else {
+                    for (int c = 0; c < C; ++c) atomicAdd(g_feats + p * C + c, w * __ldg(g_weighted + (i * K + k) * C + c));
+                }
+            }
+            if (!BWD) {
+#pragma unroll
+                for (int c = 0; c < kKpMaxC; ++c) {
+                    if (c < C) {   // C is warp-uniform
+                        float v = acc[c];
+#pragma unroll
+                        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                        if (lane == 0) weighted[(i * K + k) * C + c] = v;
+                    }
+                }
+            }
+        }
+    }
+}
+
 }  // namespace stb200
 
 using namespace stb200;
@@ -330,3 +390,31 @@ int stb200_layer_norm_backward(long long N, int C, const float *grad_y, const fl
 }
 
 }  // extern "C"
+
+extern "C" int stb200_kpconv_weighted(int n, int n_sup, int nn, int K, int C, float extent, const float *q_xyz, const float *s_xyz,
+                                      const long long *nbr, const float *kpts, const float *feats, float *weighted, void *stream) {
+    STB200_REQUIRE(n >= 0 && n_sup > 0 && nn > 0 && K > 0 && K <= kKpMaxK && C > 0 && C <= kKpMaxC && extent > 0.f, STB200_ERR_ARG,
+                   "kpconv: K <= %d kernel points, C <= %d channels (got %d, %d)", kKpMaxK, kKpMaxC, K, C);
+    if (n == 0) return STB200_OK;
+    STB200_REQUIRE(q_xyz && s_xyz && nbr && kpts && feats && weighted, STB200_ERR_ARG, "null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    KernelScope ks("kpconv_weighted_fwd", 0.0, s);
+    const int grid = (int)min((long long)kNumSMs * 8, ((long long)n + 7) / 8);
+    kpconv_weighted_kernel<false><<<grid, 256, 0, s>>>(n, n_sup, nn, K, C, 1.0f / extent, q_xyz, s_xyz, nbr, kpts, feats, weighted, nullptr, nullptr);
+    return check_launch("kpconv_weighted");
+}
+
+extern "C" int stb200_kpconv_weighted_backward(int n, int n_sup, int nn, int K, int C, float extent, const float *q_xyz, const float *s_xyz,
+                                               const long long *nbr, const float *kpts, const float *grad_weighted, float *grad_feats,
+                                               void *stream) {
+    STB200_REQUIRE(n >= 0 && n_sup > 0 && nn > 0 && K > 0 && K <= kKpMaxK && C > 0 && C <= kKpMaxC && extent > 0.f, STB200_ERR_ARG,
+                   "kpconv: K <= %d kernel points, C <= %d channels (got %d, %d)", kKpMaxK, kKpMaxC, K, C);
+    if (n == 0) return STB200_OK;
+    STB200_REQUIRE(q_xyz && s_xyz && nbr && kpts && grad_weighted && grad_feats, STB200_ERR_ARG, "null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    KernelScope ks("kpconv_weighted_bwd", 0.0, s);
+    const int grid = (int)min((long long)kNumSMs * 8, ((long long)n + 7) / 8);
+    kpconv_weighted_kernel<true><<<grid, 256, 0, s>>>(n, n_sup, nn, K, C, 1.0f / extent, q_xyz, s_xyz, nbr, kpts, nullptr, nullptr, grad_weighted,
+                                                     grad_feats);
+    return check_launch("kpconv_weighted_backward");
+}

@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 from torch.nn.init import trunc_normal_
 
+from . import pointops
 from .layers import BasicLayer, TransitionDown, Upsample
 
 
@@ -64,6 +65,14 @@ class KPConvLayer(nn.Module):
         nn.init.xavier_normal_(self.weight)
 
     def forward(self, query_points, support_points, neighbors, x):
+        if x.is_cuda and x.shape[1] <= 16 and self.n_kernel_points <= 16:
+            # neighbourhood sums in one kernel (no [n, nn, K, 3] intermediates), then ONE GEMM over (kernel point, channel)
+            wsum = pointops.kpconv_weighted(query_points, support_points, neighbors, self.K_points, x, self.point_influence)
+            return torch.matmul(wsum.reshape(wsum.shape[0], -1), self.weight.reshape(-1, self.weight.shape[-1]))
+        return self.forward_torch(query_points, support_points, neighbors, x)
+
+    def forward_torch(self, query_points, support_points, neighbors, x):
+        """the published algorithm as torch operators (the specification of the kernel path above)"""
         n_sup = support_points.shape[0]
         nb = neighbors.long()
         nb = torch.where(nb < 0, torch.full_like(nb, n_sup), nb)                       # padding -> the shadow row

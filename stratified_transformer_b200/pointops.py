@@ -429,6 +429,41 @@ def layer_norm(x, weight, bias, eps=1e-5):
     return LayerNormShortRows.apply(x, weight, bias, eps)
 
 
+class KPConvWeighted(Function):
+    """weighted[i, k, :] = sum_j max(0, 1 - |s_xyz[nbr[i,j]] - q_xyz[i] - K_k| / extent) * feats[nbr[i,j], :] (include/stb200.h:
+    stb200_kpconv_weighted); gradient only with respect to feats."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, q_xyz, s_xyz, nbr, kpts, feats, extent):
+        q_xyz, s_xyz, kpts, feats = (t.contiguous() for t in (q_xyz, s_xyz, kpts, feats))
+        nbr = nbr.long().contiguous()
+        n, nn, K, C = q_xyz.shape[0], nbr.shape[1], kpts.shape[0], feats.shape[1]
+        weighted = torch.empty(n, K, C, dtype=torch.float32, device=feats.device)
+        _cabi.call("stb200_kpconv_weighted", n, s_xyz.shape[0], nn, K, C, float(extent), q_xyz.data_ptr(), s_xyz.data_ptr(), nbr.data_ptr(),
+                   kpts.data_ptr(), feats.data_ptr(), weighted.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        ctx.save_for_backward(q_xyz, s_xyz, nbr, kpts)
+        ctx.extent, ctx.feat_shape = float(extent), feats.shape
+        return weighted
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, gw):
+        if not ctx.needs_input_grad[4]:
+            return None, None, None, None, None, None
+        q_xyz, s_xyz, nbr, kpts = ctx.saved_tensors
+        gw = gw.float().contiguous()
+        n, nn, K, C = q_xyz.shape[0], nbr.shape[1], kpts.shape[0], ctx.feat_shape[1]
+        gf = torch.zeros(ctx.feat_shape, dtype=torch.float32, device=gw.device)
+        _cabi.call("stb200_kpconv_weighted_backward", n, s_xyz.shape[0], nn, K, C, ctx.extent, q_xyz.data_ptr(), s_xyz.data_ptr(),
+                   nbr.data_ptr(), kpts.data_ptr(), gw.data_ptr(), gf.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        return None, None, None, None, gf, None
+
+
+def kpconv_weighted(q_xyz, s_xyz, nbr, kpts, feats, extent):
+    return KPConvWeighted.apply(q_xyz, s_xyz, nbr, kpts, feats, extent)
+
+
 _QKV_DTYPES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 
 

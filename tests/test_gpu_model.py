@@ -74,3 +74,29 @@ def test_whole_model_matches_reference_wiring():
     assert set(g_g) == set(w_g)
     worst = max((float((g_g[n] - w_g[n]).abs().max()) / max(1e-6, float(w_g[n].abs().max())), n) for n in w_g)
     assert worst[0] < 2e-2, f"gradient of {worst[1]}: relative max err {worst[0]:.3e}"
+
+
+@pytest.mark.parametrize("cin,cout", [(6, 48), (12, 12)])
+def test_kpconv_kernel_matches_the_torch_restatement(cin, cout):
+    """KPConvLayer.forward (neighbourhood kernel + one GEMM) against KPConvLayer.forward_torch, forward and gradients"""
+    from stratified_transformer_b200 import prestep
+    from stratified_transformer_b200.model import KPConvLayer
+    from stratified_transformer_b200.synthetic import make_batch
+    xyz, _, offset = make_batch(2, 4000, seed0=3, n_raw=100000)
+    xd, od = torch.from_numpy(xyz).cuda(), torch.from_numpy(offset).cuda()
+    batch = prestep.batch_from_offset(od)
+    nbr = prestep.ball_query(0.1, 34, xd, xd, batch_x=batch, batch_y=batch)[0]
+    torch.manual_seed(0)
+    layer = KPConvLayer(cin, cout, point_influence=0.04).cuda()
+    x1 = torch.randn(xd.shape[0], cin, device="cuda", requires_grad=True)
+    x2 = x1.detach().clone().requires_grad_(True)
+    g = torch.randn(xd.shape[0], cout, device="cuda")
+    y1 = layer(xd, xd, nbr, x1)
+    y1.backward(g)
+    gw1 = layer.weight.grad.clone()
+    layer.zero_grad()
+    y2 = layer.forward_torch(xd, xd, nbr, x2)
+    y2.backward(g)
+    for a, b, name in ((y1, y2, "out"), (x1.grad, x2.grad, "grad_feats"), (gw1, layer.weight.grad, "grad_weight")):
+        scale = max(1.0, float(b.abs().max()))
+        assert float((a - b).abs().max()) <= 2e-4 * scale, name

@@ -225,7 +225,7 @@ def ref_model_leg(dev, reps=2):
     """Whole-network like-for-like baseline ("whole model"): the reference's own `Stratified` (S3DIS configuration, its
     Python, its autograd functions, its kernels: oracle/_ref/ref_model_native.py) against `stratified_transformer_b200.model.Stratified`,
     forward + backward on ONE 80k-point scene, same state dict, same inputs (neighbour lists from prestep.ball_query on both sides).
-    torch_points3d's KPConvLayer is this package's torch restatement on both sides; tests/test_gpu_model.py checks the two agree."""
+    torch_points3d's KPConvLayer is this package's restatement on both sides; tests/test_gpu_model.py checks the two agree."""
     import importlib.util
     path = os.path.join(ROOT, "oracle", "_ref", "ref_model_native.py")
     if not (os.path.exists(path) and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libpointops2_ref.so"))):
@@ -269,7 +269,7 @@ def ref_model_leg(dev, reps=2):
                         "config/s3dis/s3dis_stratified_transformer.yaml) fwd+bwd, 1 synthetic 80k-pt scene",
             "ref_ms": round(ref_ms, 2), "ours_ms": round(ours_ms, 2), "speedup": round(ref_ms / ours_ms, 2),
             "points_per_s_ours": round(xd.shape[0] / (ours_ms * 1e-3)), "points_per_s_ref": round(xd.shape[0] / (ref_ms * 1e-3)),
-            "note": "wall clock with a device synchronize on both sides; the KPConv stem is the same torch restatement on both sides"}
+            "note": "wall clock with a device synchronize on both sides; the KPConv stem is this package's restated KPConvLayer on both sides"}
 
 
 def full_model_leg(dev, scenes, points, reps=3):
@@ -277,8 +277,8 @@ def full_model_leg(dev, scenes, points, reps=3):
     Upsample chain, classifier + offset regressor: `stratified_transformer_b200.model.Stratified`, S3DIS configuration of
     config/s3dis/s3dis_stratified_transformer.yaml) forward + backward on `scenes` x `points`-pt synthetic scenes, device-resident
     inputs, bf16 autocast around the Linear layers as in the reference's AMP recipe, radius neighbour lists (prestep.ball_query)
-    rebuilt every step like train.py:319-325 does.  Reported next to the hot-path metric, not instead of it: the stem's KPConv is
-    torch plumbing (restated third-party class), only the attention path, FPS, kNN and the index construction are this library."""
+    rebuilt every step like train.py:319-325 does.  Reported next to the hot-path metric, not instead of it: the MLPs, heads and grouping gathers are torch
+    plumbing; the attention path, FPS, kNN, the index construction, LayerNorm and the KPConv neighbourhood sums are this library."""
     from stratified_transformer_b200 import prestep
     from stratified_transformer_b200.model import Stratified
     from stratified_transformer_b200.synthetic import make_batch
@@ -311,7 +311,7 @@ def full_model_leg(dev, scenes, points, reps=3):
     return {"workload": f"full S3DIS Stratified Transformer fwd+bwd, {scenes}x{points}-pt synthetic scenes, 1 GPU (BASELINE configs[1] as written)",
             "ms_per_step": round(ms, 2), "value": round(n / (ms * 1e-3)), "unit": "points/s", "steps": reps,
             "peak_memory_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1),
-            "note": "wall clock with a device synchronize on both sides; bf16 autocast; stem KPConv = torch operators"}
+            "note": "wall clock with a device synchronize on both sides; bf16 autocast; the stem's KPConvLayer is a restated third-party class"}
 
 
 def ref_cuda_leg(dev, reps=10):

@@ -7,7 +7,8 @@ reference checkpoint's `state_dict` loads.
 here from the published algorithm (rigid KPConv, linear influence, sum aggregation; Thomas et al. 2019 / torch_points3d
 `KPConv/kernels.py`, `convolution_ops.py`) with the library's parameter names (`K_points`, `weight`, `batch_norm.*`).  The
 kernel-point disposition the library loads from its optimised tables is replaced by a fixed symmetric one for fresh models;
-checkpoints bring their own `K_points`.  These stem blocks are plain torch operators: they are outside the hot path.
+checkpoints bring their own `K_points`.  The stem is outside the hot path; its neighbourhood sums run in one kernel
+(`pointops.kpconv_weighted`), the published formula as torch operators stays as `KPConvLayer.forward_torch`.
 """
 from __future__ import annotations
 

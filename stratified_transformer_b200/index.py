@@ -249,7 +249,7 @@ def fps_new_offset(offset: torch.Tensor, downsample_scale: int) -> torch.Tensor:
     return torch.cumsum(torch.div(counts, downsample_scale, rounding_mode="floor") + 1, 0).to(torch.int32)
 
 
-def fps_prefix(long_idx: torch.Tensor, long_offset: torch.Tensor, short_offset: torch.Tensor) -> torch.Tensor:
+def fps_prefix(long_idx: torch.Tensor, long_offset: torch.Tensor, short_offset: torch.Tensor, total: int | None = None) -> torch.Tensor:
     """Furthest point sampling is greedy from point 0 of every scene, so the picks for a smaller sample count are the first
     picks of a longer run over the same scenes.  long_idx: picks of the longer run, long_offset / short_offset: cumulative counts
     per scene of the longer / the wanted run (short count <= long count in every scene).  Returns the shorter run's picks."""
@@ -258,8 +258,10 @@ def fps_prefix(long_idx: torch.Tensor, long_offset: torch.Tensor, short_offset: 
     long_start = lo - torch.diff(lo, prepend=lo.new_zeros(1))
     short_cnt = torch.diff(so, prepend=so.new_zeros(1))
     short_start = so - short_cnt
-    scene = torch.repeat_interleave(torch.arange(so.numel(), device=lo.device), short_cnt)
-    pos = torch.arange(int(so[-1]), device=lo.device) - short_start[scene] + long_start[scene]
+    if total is None:
+        total = int(so[-1])        # host sync; pass `total` (the last entry of short_offset) to stay asynchronous
+    scene = torch.repeat_interleave(torch.arange(so.numel(), device=lo.device), short_cnt, output_size=total)
+    pos = torch.arange(total, device=lo.device) - short_start[scene] + long_start[scene]
     return long_idx[pos].contiguous()
 
 

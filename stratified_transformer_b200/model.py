@@ -18,8 +18,10 @@ import torch
 import torch.nn as nn
 from torch.nn.init import trunc_normal_
 
+from . import index as st_index
 from . import pointops
-from .layers import BasicLayer, TransitionDown, Upsample
+from . import prestep
+from .layers import BasicLayer, TransitionDown, Upsample, transition_down_offsets
 
 
 def default_kernel_points(radius: float, n: int = 15) -> torch.Tensor:
@@ -171,19 +173,23 @@ class Stratified(nn.Module):
                                        nn.Linear(channels[0], 3))
         self.init_weights()
 
-    def forward(self, feats, xyz, offset, batch, neighbor_idx):
-        # (Building every layer's sampling + pair lists on a side stream under the stem was tried: 155.7 -> 154.0 ms on 8 x 80k
-        # points - the sampling clusters take their SMs from the stem's bandwidth-bound kernels - and dropped for simplicity.
-        # A training loop overlaps the geometry of the NEXT batch instead: index.GeometryPrefetcher.)
+    def forward(self, feats, xyz, offset, batch, neighbor_idx, geometry=None):
+        """geometry: what `GeometryChain.take()` returns for this batch (sampling + pair lists of every layer, prefetched on a side
+        stream during the previous step); None builds them inline, layer by layer."""
+        # (Building them on a side stream under the stem of the SAME step was tried: 155.7 -> 154.0 ms on 8 x 80k points - the
+        # sampling clusters take their SMs from the stem's bandwidth-bound kernels.  Across steps it pays: GeometryChain.)
+        stages = iter(geometry["stages"]) if geometry is not None else None
         stack = []
         for layer in self.stem_layer:
             feats = layer(feats, xyz, batch, neighbor_idx)
         feats = feats.contiguous()
         if self.layer_start == 1:
             stack.append((feats, xyz, offset))
-            feats, xyz, offset = self.downsample(feats, xyz, offset)
+            fps = next(stages)[1] if stages is not None else None
+            feats, xyz, offset = self.downsample(feats, xyz, offset, fps)
         for layer in self.layers:
-            feats, xyz, offset, feats_down, xyz_down, offset_down = layer(feats, xyz, offset)
+            li, fps = next(stages) if stages is not None else (None, None)
+            feats, xyz, offset, feats_down, xyz_down, offset_down = layer(feats, xyz, offset, layer_index=li, fps=fps)
             stack.append((feats, xyz, offset))
             feats, xyz, offset = feats_down, xyz_down, offset_down
         feats, xyz, offset = stack.pop()
@@ -202,3 +208,109 @@ class Stratified(nn.Module):
                 nn.init.constant_(m.bias, 0)
                 nn.init.constant_(m.weight, 1.0)
         self.apply(_init)
+
+
+class GeometryChain:
+    """Everything `Stratified.forward` derives from the coordinates alone, for one batch, on a side stream: the per-point scene id and
+    the radius neighbour lists of the stem (train.py:319-325), and per layer TransitionDown's furthest-point picks, the stratified key
+    candidates (their prefix) and the pair lists of both block parities.  None of it depends on features, so the chain of batch t+1
+    can run under the compute of batch t (the sampling loops are long sequential kernels on a few SMs).  Measured on the full
+    S3DIS network, 8 x 80k points: 143.2 -> 141.6 ms per step - the sampling clusters mostly wait for SMs - so `bench.py` does not use it:
+
+        chain = GeometryChain(model); chain.submit(xyz0, offset0, radius)
+        for batch in loader:
+            geo = chain.take()                                  # current batch: main stream waits for its events
+            out = model(feats, xyz, offset, geo["batch"], geo["neighbor_idx"], geometry=geo)
+            chain.submit(next_xyz, next_offset, radius)         # between forward and backward works best
+            loss.backward(); chain.complete()                   # host: sizes of the pair lists, then their fill kernels
+    """
+
+    def __init__(self, model: Stratified, max_neighbors: int = 34):
+        self.model, self.max_neighbors = model, max_neighbors
+        self.side = None
+        self.pending = self.done = None
+
+    def submit(self, xyz, offset, radius=None):
+        model = self.model
+        main = torch.cuda.current_stream()
+        if self.side is None:
+            self.side = torch.cuda.Stream(device=xyz.device)
+        side = self.side
+        side.wait_stream(main)
+        xyz.record_stream(side)
+        off_host = [int(v) for v in offset.tolist()]
+        stages = []
+        with torch.cuda.stream(side):
+            off_t = offset.to(torch.int32).contiguous()
+            batch = prestep.batch_from_offset(off_t, xyz.shape[0])
+            nbr = None
+            if radius is not None:
+                nbr = prestep.ball_query(radius, self.max_neighbors, xyz, xyz, mode="partial_dense", batch_x=batch, batch_y=batch)[0]
+            downs = ([model.downsample] if model.layer_start == 1 else []) + [None] * len(model.layers)
+            layers = ([None] if model.layer_start == 1 else []) + list(model.layers)
+            for pre, layer in zip(downs, layers):
+                td = pre if layer is None else layer.downsample
+                fps = n_off_t = pend = n_host = None
+                if isinstance(td, TransitionDown):
+                    n_host = transition_down_offsets(off_host, td.ratio)
+                    n_off_t = torch.tensor(n_host, dtype=torch.int32, device=xyz.device)
+                if layer is not None:
+                    ds = layer.downsample_scale
+                    k_host, c = [], 0
+                    for i, o in enumerate(off_host):
+                        c += (o - (off_host[i - 1] if i else 0)) // ds + 1
+                        k_host.append(c)
+                    k_off_t = torch.tensor(k_host, dtype=torch.int32, device=xyz.device)
+                    prefix_ok = n_host is not None and all(
+                        (k_host[i] - (k_host[i - 1] if i else 0)) <= (n_host[i] - (n_host[i - 1] if i else 0)) for i in range(len(k_host)))
+                    if prefix_ok:
+                        fps = self._fps(xyz, off_t, off_host, n_off_t, n_host)
+                        ds_idx = st_index.fps_prefix(fps, n_off_t, k_off_t, total=k_host[-1])
+                    else:
+                        ds_idx = self._fps(xyz, off_t, off_host, k_off_t, k_host)
+                    pend = st_index.PendingLayerIndex(xyz, off_t, layer.window_size, layer.quant_size, ds, off_host, fused=layer.fused,
+                                                      downsample_idx=ds_idx)
+                if n_host is not None and fps is None:
+                    fps = self._fps(xyz, off_t, off_host, n_off_t, n_host)
+                stages.append((fps, n_off_t, pend))
+                if fps is not None:
+                    xyz = xyz[fps.long(), :].contiguous()
+                    off_t, off_host = n_off_t, n_host
+            event = side.record_event()
+        self.pending = (batch, nbr, stages, event)
+
+    @staticmethod
+    def _fps(xyz, off_t, off_host, new_off_t, new_host):
+        """pointops.furthestsampling without its device-to-host read: the sizes are known on the host here, and a synchronisation
+        inside submit() would keep the host from enqueueing the step's backward pass while the sampling loop runs"""
+        from . import pointops2_cuda as ext
+        n_max = max(o - (off_host[i - 1] if i else 0) for i, o in enumerate(off_host))
+        idx = torch.zeros(int(new_host[-1]), dtype=torch.int32, device=xyz.device)
+        ext.furthestsampling_cuda(len(off_host), n_max, xyz.contiguous(), off_t, new_off_t, None, idx)
+        return idx
+
+    def complete(self):
+        if self.pending is None:
+            return
+        batch, nbr, stages, event = self.pending
+        with torch.cuda.stream(self.side):
+            done = [(None if pend is None else pend.finish(), None if fps is None else (fps, n_off)) for fps, n_off, pend in stages]
+            event = self.side.record_event()
+        self.done, self.pending = (batch, nbr, done, event), None
+
+    def take(self):
+        if self.done is None:
+            self.complete()
+        (batch, nbr, done, event), self.done = self.done, None
+        main = torch.cuda.current_stream()
+        main.wait_event(event)
+        for t in (batch, nbr):
+            if t is not None:
+                t.record_stream(main)
+        for li, fps in done:
+            if li is not None:
+                st_index.record_stream(li, main)
+            if fps is not None:
+                fps[0].record_stream(main)
+                fps[1].record_stream(main)
+        return {"batch": batch, "neighbor_idx": nbr, "stages": done}

@@ -100,3 +100,21 @@ def test_kpconv_kernel_matches_the_torch_restatement(cin, cout):
     for a, b, name in ((y1, y2, "out"), (x1.grad, x2.grad, "grad_feats"), (gw1, layer.weight.grad, "grad_weight")):
         scale = max(1.0, float(b.abs().max()))
         assert float((a - b).abs().max()) <= 2e-4 * scale, name
+
+
+def test_prefetched_geometry_gives_the_same_network_output():
+    """model.GeometryChain (sampling + pair lists + neighbour lists of a batch on a side stream) against the inline construction"""
+    from stratified_transformer_b200.model import GeometryChain, Stratified
+    torch.manual_seed(5)
+    model = Stratified(**CFG).cuda()
+    feat, xd, od, batch, nbr = _inputs()
+    with torch.no_grad():
+        want_out, want_shift = model(feat, xd, od, batch, nbr)
+        chain = GeometryChain(model)
+        for _ in range(2):                       # twice: the second round reuses the chain's stream and buffers
+            chain.submit(xd, od, 2.5 * 0.04)
+            geo = chain.take()
+            assert torch.equal(geo["batch"], batch) and torch.equal(geo["neighbor_idx"], nbr)
+            out, shift = model(feat, xd, od, geo["batch"], geo["neighbor_idx"], geometry=geo)
+            torch.cuda.synchronize()
+            assert torch.equal(out, want_out) and torch.equal(shift, want_shift)
